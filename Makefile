@@ -1,0 +1,34 @@
+# Builds the product library stt_b200/libstt_b200.so (CUDA sm_100a + C++ host, no CPU path) and, via
+# `make oracle`, the test-only oracle libraries.  __graft_entry__.build() drives both.
+NVCC      ?= nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v
+CXXFLAGS  := -O2 -std=c++17 -fPIC -fvisibility=hidden -mfma -ffp-contract=off
+CUDA_HOME ?= /usr/local/cuda
+SRC       := stt_b200/csrc
+OUT       := stt_b200/libstt_b200.so
+BUILD     := build
+
+HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/stt_capi.h
+
+.PHONY: all oracle clean
+all: $(OUT)
+
+$(BUILD)/engine.o: $(SRC)/engine.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/ptxas_engine.log || (cat $(BUILD)/ptxas_engine.log; false)
+
+$(BUILD)/%.o: $(SRC)/%.cc $(HDRS)
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -I$(CUDA_HOME)/include -c $< -o $@
+
+$(OUT): $(BUILD)/engine.o $(BUILD)/capi.o $(BUILD)/model_file.o $(BUILD)/scorer_image.o
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -Xlinker --exclude-libs,ALL
+
+oracle:
+	$(MAKE) -C oracle
+	if [ -d /root/reference ]; then $(MAKE) -C oracle -j8 ref; fi
+
+clean:
+	rm -rf $(BUILD) $(OUT)

@@ -1,0 +1,1054 @@
+// See engine.h.  Host orchestration + kernel launches; every numeric step cites the reference in the kernel headers.
+#include "engine.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "decoder.cuh"
+#include "gemm_tc.cuh"
+#include "lstm_tc.cuh"
+#include "mfcc.cuh"
+#include "scorer_image.h"
+
+namespace stteng {
+
+#define CUDA_OK(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      fprintf(stderr, "[stt_b200] CUDA error %s at %s:%d: %s\n", #expr, __FILE__, __LINE__,            \
+              cudaGetErrorString(_e));                                                                  \
+      return -1;                                                                                        \
+    }                                                                                                   \
+  } while (0)
+
+namespace {
+
+// ------------------------------------------------------------------ small device helpers
+__global__ void f32_to_f16_kernel(const float* in, __half* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+__global__ void shift_frames_kernel(__half* feat, int n_keep, int shift, int lanes, int total_frames) {
+  // feat[f] = feat[f + shift] for f < n_keep, zero the rest; single block, sequential in f to allow overlap
+  for (int f = 0; f < total_frames; ++f) {
+    for (int l = threadIdx.x; l < lanes; l += blockDim.x) {
+      __half v = (f < n_keep) ? feat[(size_t)(f + shift) * lanes + l] : __float2half_rn(0.f);
+      feat[(size_t)f * lanes + l] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// Fallback only: materialise the stacked-context windows if the driver refuses the overlapping-row tensor map.
+__global__ void gather_windows_kernel(const __half* feat, __half* out, int B, int T, int rows_per_utt, int K1, int K1p) {
+  const size_t row = blockIdx.x;  // t * B + b
+  const int t = (int)(row / B), b = (int)(row % B);
+  const __half* src = feat + ((size_t)b * rows_per_utt + t) * sttmfcc::kFeatLanes;
+  for (int k = threadIdx.x; k < K1p; k += blockDim.x) out[row * K1p + k] = (k < K1) ? src[k] : __float2half_rn(0.f);
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// fp16 tensor map, innermost dimension contiguous, 128B swizzle, box inner = 64 elements.
+bool make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[3], gstride[2];
+  cuuint32_t bdim[3], estr[3];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[stt_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
+    return false;
+  }
+  return true;
+}
+bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                  uint32_t box_rows) {
+  uint64_t dims[2] = {cols, rows}, strides[1] = {row_stride_elems * 2};
+  uint32_t box[2] = {64, box_rows};
+  return make_tmap(out, base, 2, dims, strides, box);
+}
+
+template <int BN, int EPI, int AMODE>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::GemmParams& p, int num_sms,
+                cudaStream_t st) {
+  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  using L = sttgemm::SmemLayout<BN, STAGES>;
+  auto kern = sttgemm::gemm_tc_kernel<BN, STAGES, EPI, AMODE>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  int n_tiles_m;
+  if (AMODE == sttgemm::kWindows3D)
+    n_tiles_m = ((p.T + p.t_box - 1) / p.t_box) * ((p.B + p.b_box - 1) / p.b_box);
+  else
+    n_tiles_m = (p.M + sttgemm::BLOCK_M - 1) / sttgemm::BLOCK_M;
+  const int n_tiles = n_tiles_m * (p.N / BN);
+  const int grid = std::max(1, std::min(n_tiles, num_sms));
+  kern<<<grid, sttgemm::kNumThreads, L::kTotal, st>>>(ta, tb, p);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// ====================================================================================== Engine
+struct Engine {
+  sttmodel::HostModel hm;
+  int device = 0, num_sms = 0;
+  int Hp = 0, Cp = 0, K1 = 0;  // padded hidden / cell dims, layer-1 K (= (2c+1)*32)
+  // weights: [N, K] fp16 K-major
+  __half *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wx = nullptr, *wh = nullptr, *w5 = nullptr, *w6 = nullptr;
+  float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *bx = nullptr, *b5 = nullptr, *b6 = nullptr;
+  CUtensorMap tm_w1, tm_w2, tm_w3, tm_wx, tm_wh, tm_w5, tm_w6;
+  // MFCC tables
+  sttmfcc::MfccTables tables{};
+  std::vector<void*> table_allocs;
+  // scorer
+  bool has_scorer = false;
+  uint8_t* scorer_blob = nullptr;
+  sttscorer::ScorerView scorer_view{};
+};
+
+const sttmodel::HostModel& engine_model(const Engine* e) { return e->hm; }
+bool engine_has_scorer(const Engine* e) { return e->has_scorer; }
+int engine_num_sms(const Engine* e) { return e->num_sms; }
+void engine_set_alpha_beta(Engine* e, float alpha, float beta) {
+  e->scorer_view.alpha = (double)alpha;  // Scorer::reset_params(float, float), scorer.cpp:346-351
+  e->scorer_view.beta = (double)beta;
+}
+
+namespace {
+
+template <class T>
+int upload(T** dst, const std::vector<T>& src, std::vector<void*>* track = nullptr) {
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(dst), std::max<size_t>(src.size(), 1) * sizeof(T)));
+  CUDA_OK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (track) track->push_back(*dst);
+  return 0;
+}
+
+// W[in, out] fp32 (TF layout) -> [Np, Kp] fp16 K-major, zero padded; optional row permutation of the output dim.
+std::vector<__half> to_nk_f16(const float* W, int n_in, int n_out, int Kp, int Np) {
+  std::vector<__half> o((size_t)Np * Kp, __float2half_rn(0.f));
+  for (int k = 0; k < n_in; ++k)
+    for (int n = 0; n < n_out; ++n) o[(size_t)n * Kp + k] = __float2half_rn(W[(size_t)k * n_out + n]);
+  return o;
+}
+
+int build_mfcc_tables(Engine* e) {
+  const auto& m = e->hm;
+  if ((int)m.win_len > sttmfcc::kFft) return -1;
+  // fft length = NextPowerOfTwo(window) (spectrogram.cc:92): the kernel is specialised for 512
+  int fft = 1;
+  while (fft < (int)m.win_len) fft <<= 1;
+  if (fft != sttmfcc::kFft) return -1;
+  const int n_bins = sttmfcc::kBins, n_ch = 40, n_dct = (int)m.n_input;
+  const double pi = atan(1.0) * 4.0;
+  std::vector<double> hann(m.win_len), tw_re(256), tw_im(256);
+  for (uint32_t i = 0; i < m.win_len; ++i) hann[i] = 0.5 - 0.5 * cos((2.0 * pi * i) / m.win_len);
+  for (int k = 0; k < 256; ++k) {
+    const double ang = -2.0 * pi * k / 512.0;
+    tw_re[k] = cos(ang);
+    tw_im[k] = sin(ang);
+  }
+  // MfccMelFilterbank::Initialize (mfcc_mel_filterbank.cc:40-167): lower 20 Hz, upper sample_rate/2, 40 channels
+  const double lower = 20.0, upper = m.sample_rate / 2, sr = m.sample_rate;
+  auto mel = [](double f) { return 1127.0 * log1p(f / 700.0); };
+  std::vector<double> center(n_ch + 1), weights(n_bins);
+  std::vector<int> mapper(n_bins), first(n_ch, -1), last(n_ch, -1);
+  const double mel_low = mel(lower), mel_hi = mel(upper), spacing = (mel_hi - mel_low) / (double)(n_ch + 1);
+  for (int i = 0; i < n_ch + 1; ++i) center[i] = mel_low + spacing * (i + 1);
+  const double hz_per_sbin = 0.5 * sr / (double)(n_bins - 1);
+  const int start_index = (int)(1.5 + lower / hz_per_sbin), end_index = (int)(upper / hz_per_sbin);
+  int channel = 0;
+  for (int i = 0; i < n_bins; ++i) {
+    const double melf = mel(i * hz_per_sbin);
+    if (i < start_index || i > end_index) {
+      mapper[i] = -2;
+    } else {
+      while (channel < n_ch && center[channel] < melf) ++channel;
+      mapper[i] = channel - 1;
+    }
+  }
+  for (int i = 0; i < n_bins; ++i) {
+    channel = mapper[i];
+    if (i < start_index || i > end_index) weights[i] = 0.0;
+    else if (channel >= 0)
+      weights[i] = (center[channel + 1] - mel(i * hz_per_sbin)) / (center[channel + 1] - center[channel]);
+    else
+      weights[i] = (center[0] - mel(i * hz_per_sbin)) / (center[0] - mel_low);
+  }
+  for (int i = start_index; i <= end_index && i < n_bins; ++i) {
+    for (int ch : {mapper[i], mapper[i] + 1}) {
+      if (ch < 0 || ch >= n_ch) continue;
+      if (first[ch] < 0) first[ch] = i;
+      last[ch] = i;
+    }
+  }
+  std::vector<double> cosines((size_t)n_dct * n_ch);
+  const double fnorm = sqrt(2.0 / n_ch), arg = pi / n_ch;
+  for (int i = 0; i < n_dct; ++i)
+    for (int j = 0; j < n_ch; ++j) cosines[(size_t)i * n_ch + j] = fnorm * cos(i * arg * (j + 0.5));
+
+  double *d_hann, *d_re, *d_im, *d_w, *d_cos;
+  int *d_map, *d_first, *d_last;
+  if (upload(&d_hann, hann, &e->table_allocs) || upload(&d_re, tw_re, &e->table_allocs) ||
+      upload(&d_im, tw_im, &e->table_allocs) || upload(&d_w, weights, &e->table_allocs) ||
+      upload(&d_cos, cosines, &e->table_allocs) || upload(&d_map, mapper, &e->table_allocs) ||
+      upload(&d_first, first, &e->table_allocs) || upload(&d_last, last, &e->table_allocs))
+    return -1;
+  e->tables = sttmfcc::MfccTables{d_hann, d_re,    d_im,     d_w,          d_map,       d_first,
+                                  d_last, d_cos,   (int)m.win_len, (int)m.win_step, n_ch, n_dct,
+                                  start_index, end_index};
+  return 0;
+}
+
+int build_weights(Engine* e) {
+  const auto& m = e->hm;
+  const int H = m.n_hidden, C = m.n_cell, K = m.n_classes, ni = m.n_input, nf = 2 * m.n_context + 1;
+  e->Hp = round_up(H, 256);
+  e->Cp = round_up(C, 64);
+  e->K1 = nf * sttmfcc::kFeatLanes;
+  const int Hp = e->Hp, Cp = e->Cp, K1p = round_up(e->K1, 64);
+  // layer 1: K index f*32 + i  <-  row (f*n_input + i) of w1
+  std::vector<__half> w1((size_t)Hp * K1p, __float2half_rn(0.f));
+  for (int f = 0; f < nf; ++f)
+    for (int i = 0; i < ni; ++i)
+      for (int n = 0; n < H; ++n)
+        w1[(size_t)n * K1p + f * sttmfcc::kFeatLanes + i] = __float2half_rn(m.w1[(size_t)(f * ni + i) * H + n]);
+  auto pad_bias = [](const std::vector<float>& b, int Np) {
+    std::vector<float> o(Np, 0.f);
+    std::copy(b.begin(), b.end(), o.begin());
+    return o;
+  };
+  std::vector<__half> w2 = to_nk_f16(m.w2.data(), H, H, Hp, Hp), w3 = to_nk_f16(m.w3.data(), H, H, Hp, Hp);
+  std::vector<__half> w5 = to_nk_f16(m.w5.data(), C, H, Cp, Hp);
+  std::vector<__half> w6 = to_nk_f16(m.w6.data(), H, K, Hp, 32);
+  // LSTM kernel [H + C, 4C], gate blocks i|j|f|o (rnn_cell_impl.py:1060-1061) -> gate-interleaved rows cell*4 + g
+  std::vector<__half> wx((size_t)4 * Cp * Hp, __float2half_rn(0.f)), wh((size_t)4 * Cp * Cp, __float2half_rn(0.f));
+  std::vector<float> bx((size_t)4 * Cp, 0.f);
+  for (int cell = 0; cell < C; ++cell)
+    for (int g = 0; g < 4; ++g) {
+      const size_t row = (size_t)cell * 4 + g;
+      const size_t col = (size_t)g * C + cell;
+      for (int k = 0; k < H; ++k) wx[row * Hp + k] = __float2half_rn(m.lstm_kernel[(size_t)k * 4 * C + col]);
+      for (int k = 0; k < C; ++k) wh[row * Cp + k] = __float2half_rn(m.lstm_kernel[(size_t)(H + k) * 4 * C + col]);
+      bx[row] = m.lstm_bias[col];
+    }
+  if (upload(&e->w1, w1) || upload(&e->w2, w2) || upload(&e->w3, w3) || upload(&e->wx, wx) || upload(&e->wh, wh) ||
+      upload(&e->w5, w5) || upload(&e->w6, w6))
+    return -1;
+  std::vector<float> b1 = pad_bias(m.b1, Hp), b2 = pad_bias(m.b2, Hp), b3 = pad_bias(m.b3, Hp), b5 = pad_bias(m.b5, Hp),
+                     b6 = pad_bias(m.b6, 32);
+  if (upload(&e->b1, b1) || upload(&e->b2, b2) || upload(&e->b3, b3) || upload(&e->bx, bx) || upload(&e->b5, b5) ||
+      upload(&e->b6, b6))
+    return -1;
+  bool ok = make_tmap_2d(&e->tm_w1, e->w1, Hp, K1p, K1p, 256) && make_tmap_2d(&e->tm_w2, e->w2, Hp, Hp, Hp, 256) &&
+            make_tmap_2d(&e->tm_w3, e->w3, Hp, Hp, Hp, 256) && make_tmap_2d(&e->tm_wx, e->wx, 4 * Cp, Hp, Hp, 256) &&
+            make_tmap_2d(&e->tm_wh, e->wh, 4 * Cp, Cp, Cp, 64) && make_tmap_2d(&e->tm_w5, e->w5, Hp, Cp, Cp, 256) &&
+            make_tmap_2d(&e->tm_w6, e->w6, 32, Hp, Hp, 32);
+  return ok ? 0 : -1;
+}
+
+}  // namespace
+
+Engine* engine_create(const sttmodel::HostModel& m, std::string* err) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    if (err) *err = "no CUDA device: this library has no CPU path";
+    return nullptr;
+  }
+  Engine* e = new Engine();
+  e->hm = m;
+  cudaGetDevice(&e->device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, e->device);
+  e->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    if (err) *err = "sm_100a (B200) required";
+    delete e;
+    return nullptr;
+  }
+  if (m.n_classes > 33 || m.n_classes < 2) {
+    if (err) *err = "alphabets larger than 32 labels are not supported yet";
+    delete e;
+    return nullptr;
+  }
+  if (round_up(m.n_cell, 64) / sttlstm::kCellsPerCta > e->num_sms) {
+    if (err) *err = "n_cell too large for the single-wave LSTM kernel";
+    delete e;
+    return nullptr;
+  }
+  if (build_mfcc_tables(e) != 0 || build_weights(e) != 0) {
+    if (err) *err = "failed to build device tables / weights";
+    delete e;
+    return nullptr;
+  }
+  return e;
+}
+
+void engine_clear_scorer(Engine* e) {
+  if (e->scorer_blob) cudaFree(e->scorer_blob);
+  e->scorer_blob = nullptr;
+  e->has_scorer = false;
+}
+
+void engine_destroy(Engine* e) {
+  if (!e) return;
+  engine_clear_scorer(e);
+  for (void* p : e->table_allocs) cudaFree(p);
+  for (void* p : {(void*)e->w1, (void*)e->w2, (void*)e->w3, (void*)e->wx, (void*)e->wh, (void*)e->w5, (void*)e->w6,
+                  (void*)e->b1, (void*)e->b2, (void*)e->b3, (void*)e->bx, (void*)e->b5, (void*)e->b6})
+    if (p) cudaFree(p);
+  delete e;
+}
+
+int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
+  sttscorer::AlphabetBytes ab;
+  ab.labels = e->hm.labels;
+  ab.space_label = e->hm.space_label;
+  sttscorer::ScorerView v;
+  int err = sttscorer::parse_scorer(bytes, n, ab, &v);
+  if (err) return err;
+  if (v.is_utf8) return sttscorer::SCORER_INVALID_TRIE;  // bytes-output mode: SURVEY 8(f) rank 4, not built yet
+  engine_clear_scorer(e);
+  if (cudaMalloc(reinterpret_cast<void**>(&e->scorer_blob), n + 16) != cudaSuccess) return sttscorer::SCORER_UNREADABLE;
+  cudaMemset(e->scorer_blob + n, 0, 16);
+  if (cudaMemcpy(e->scorer_blob, bytes, n, cudaMemcpyHostToDevice) != cudaSuccess) return sttscorer::SCORER_UNREADABLE;
+  v.blob = e->scorer_blob;
+  e->scorer_view = v;
+  e->has_scorer = true;
+  return 0;
+}
+
+// ====================================================================================== Batch
+struct Batch {
+  Engine* e = nullptr;
+  int B_cap = 0, S_cap = 0, T_cap = 0, beam_cap = 0, dec_T_cap = 0, max_results = 0;
+  int B = 0, T_max = 0;
+  std::vector<int> T;  // timesteps per utterance
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[12];
+  // host staging (pinned)
+  int16_t* h_pcm = nullptr;
+  int* h_nsamples = nullptr;
+  // device
+  int16_t* d_pcm = nullptr;
+  int* d_nsamples = nullptr;
+  int rows_per_utt = 0;        // T_cap + 2*n_context (+ pad)
+  __half* d_feat = nullptr;    // [B_cap, rows_per_utt, 32]
+  float* d_feat32 = nullptr;   // [B_cap, T_cap, n_input]
+  __half *d_act_a = nullptr, *d_act_b = nullptr;  // [T_cap*B_cap, Hp]
+  float* d_xw = nullptr;       // [T_cap*B_cap, 4*Cp]
+  __half* d_hall = nullptr;    // [(T_cap+1)*B_cap, Cp]
+  float *d_c = nullptr, *d_h = nullptr;  // [B_cap, Cp]
+  unsigned int* d_barrier = nullptr;
+  float* d_probs = nullptr;    // [B_cap, T_cap, n_classes]
+  CUtensorMap tm_act_a, tm_act_b, tm_hall, tm_hall_out;
+  __half* d_winmat = nullptr;  // fallback window matrix [T_cap*B_cap + 128, K1p]
+  CUtensorMap tm_winmat;
+  // decoder
+  sttdec::Slot* d_slots = nullptr;
+  std::vector<sttdec::Slot> h_slots;
+  uint8_t* d_slot_mem = nullptr;
+  size_t slot_bytes = 0;
+  sttdec::StepInput* d_inputs = nullptr;
+  sttdec::FinalOut* d_finals = nullptr;
+  uint8_t* d_out_mem = nullptr;
+  uint8_t* h_out_mem = nullptr;  // pinned mirror
+  size_t out_bytes_per_utt = 0;
+  int cur_beam = 0, cur_results = 1;
+  // streaming
+  int stream_frames = 0;  // frames currently in d_feat (utterance 0)
+  int16_t* d_win = nullptr;
+  sttmfcc::FrameJob* d_jobs = nullptr;
+  int last_run_T = 0;
+  StageTimes times;
+  long long launches = 0;
+};
+
+const StageTimes& batch_times(const Batch* b) { return b->times; }
+long long batch_kernel_launches(const Batch* b) { return b->launches; }
+int batch_T(const Batch* b, int utt) { return (utt >= 0 && utt < b->B) ? b->T[utt] : -1; }
+
+namespace {
+
+int frames_for(int n, int win_len, int win_step) { return (n >= win_len ? (n - win_len) / win_step + 1 : 0) + 1; }
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int alloc_slots(Batch* b) {
+  const int W = b->beam_cap, C = b->e->hm.n_classes;
+  const uint32_t arena_cap = 1u + (uint32_t)W * (uint32_t)b->dec_T_cap;
+  const uint32_t ts_cap = 1u + (uint32_t)W * (uint32_t)(b->dec_T_cap + 1);
+  const uint32_t cand_cap = (uint32_t)W * (uint32_t)C;
+  uint32_t ht = 1;
+  while (ht < 2u * arena_cap) ht <<= 1;
+  // carve one slab per slot
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  struct Offs {
+    size_t parent, chr, dict, lsp, wid, lslot, htk, htv, tsp, tsv, score[2], bp[2], nbp[2], node[2], ts[2], cs, ca, cb, cc,
+        cd, ck, lmt, lmw, scal;
+  } o;
+  o.parent = take(4ull * arena_cap); o.chr = take(4ull * arena_cap); o.dict = take(4ull * arena_cap);
+  o.lsp = take(4ull * arena_cap); o.wid = take(4ull * arena_cap); o.lslot = take(4ull * arena_cap);
+  o.htk = take(8ull * ht); o.htv = take(4ull * ht);
+  o.tsp = take(4ull * ts_cap); o.tsv = take(4ull * ts_cap);
+  for (int k = 0; k < 2; ++k) {
+    o.score[k] = take(4ull * W); o.bp[k] = take(4ull * W); o.nbp[k] = take(4ull * W);
+    o.node[k] = take(4ull * W); o.ts[k] = take(4ull * W);
+  }
+  o.cs = take(4ull * cand_cap); o.ca = take(4ull * cand_cap); o.cb = take(4ull * cand_cap);
+  o.cc = take(4ull * cand_cap); o.cd = take(4ull * cand_cap); o.ck = take(8ull * cand_cap);
+  o.lmt = take(4ull * W); o.lmw = take(4ull * W); o.scal = take(64);
+  b->slot_bytes = off;
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_slot_mem), b->slot_bytes * b->B_cap));
+  b->h_slots.resize(b->B_cap);
+  for (int u = 0; u < b->B_cap; ++u) {
+    uint8_t* base = b->d_slot_mem + b->slot_bytes * u;
+    sttdec::Slot& s = b->h_slots[u];
+    s.parent = (uint32_t*)(base + o.parent); s.chr = (uint32_t*)(base + o.chr); s.dict_state = (int32_t*)(base + o.dict);
+    s.last_space = (uint32_t*)(base + o.lsp); s.word_id = (uint32_t*)(base + o.wid); s.live_slot = (uint32_t*)(base + o.lslot);
+    s.ht_key = (unsigned long long*)(base + o.htk); s.ht_val = (uint32_t*)(base + o.htv); s.ht_mask = ht - 1;
+    s.ts_parent = (uint32_t*)(base + o.tsp); s.ts_val = (uint32_t*)(base + o.tsv);
+    for (int k = 0; k < 2; ++k) {
+      s.score[k] = (float*)(base + o.score[k]); s.b_prev[k] = (float*)(base + o.bp[k]); s.nb_prev[k] = (float*)(base + o.nbp[k]);
+      s.node[k] = (uint32_t*)(base + o.node[k]); s.ts[k] = (uint32_t*)(base + o.ts[k]);
+    }
+    s.c_score = (float*)(base + o.cs); s.c_a = (uint32_t*)(base + o.ca); s.c_b = (uint32_t*)(base + o.cb);
+    s.c_c = (uint32_t*)(base + o.cc); s.c_d = (uint32_t*)(base + o.cd); s.c_key = (uint64_t*)(base + o.ck);
+    s.lm_term = (float*)(base + o.lmt); s.lm_word = (uint32_t*)(base + o.lmw); s.scalars = (uint32_t*)(base + o.scal);
+    s.arena_cap = arena_cap; s.ts_cap = ts_cap; s.beam_cap = W; s.cand_cap = cand_cap;
+  }
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_slots), sizeof(sttdec::Slot) * b->B_cap));
+  CUDA_OK(cudaMemcpy(b->d_slots, b->h_slots.data(), sizeof(sttdec::Slot) * b->B_cap, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_inputs), sizeof(sttdec::StepInput) * b->B_cap));
+  // outputs: per utterance [n_results i32][pad][confidence f64 x R][n_tokens i32 x R][tokens u32 x R*Tm][timesteps ...]
+  const int R = b->max_results, Tm = b->dec_T_cap;
+  size_t per = 0;
+  per = align_up(per + 8, 8);
+  const size_t o_conf = per; per += 8ull * R;
+  const size_t o_nt = per; per += 4ull * R;
+  per = align_up(per, 8);
+  const size_t o_tok = per; per += 4ull * R * Tm;
+  const size_t o_ts = per; per += 4ull * R * Tm;
+  per = align_up(per, 256);
+  b->out_bytes_per_utt = per;
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_out_mem), per * b->B_cap));
+  CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&b->h_out_mem), per * b->B_cap));
+  std::vector<sttdec::FinalOut> fo(b->B_cap);
+  for (int u = 0; u < b->B_cap; ++u) {
+    uint8_t* base = b->d_out_mem + per * u;
+    fo[u].max_results = R; fo[u].max_tokens = Tm;
+    fo[u].n_results = (int*)base; fo[u].confidence = (double*)(base + o_conf); fo[u].n_tokens = (int*)(base + o_nt);
+    fo[u].tokens = (uint32_t*)(base + o_tok); fo[u].timesteps = (uint32_t*)(base + o_ts);
+  }
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_finals), sizeof(sttdec::FinalOut) * b->B_cap));
+  CUDA_OK(cudaMemcpy(b->d_finals, fo.data(), sizeof(sttdec::FinalOut) * b->B_cap, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // namespace
+
+Batch* batch_create(Engine* e, int B_cap, int max_samples, int beam_cap, int dec_T_cap, std::string* err) {
+  const auto& m = e->hm;
+  Batch* b = new Batch();
+  b->e = e;
+  b->B_cap = B_cap;
+  b->S_cap = std::max(max_samples, (int)m.win_len);
+  b->T_cap = frames_for(b->S_cap, m.win_len, m.win_step);
+  b->beam_cap = beam_cap;
+  b->dec_T_cap = std::max(dec_T_cap, b->T_cap);
+  b->max_results = 1;
+  b->T.assign(B_cap, 0);
+  auto fail = [&](const char* what) -> Batch* {
+    if (err) *err = what;
+    batch_destroy(b);
+    return nullptr;
+  };
+  if (B_cap > 256) return fail("B_cap > 256: split the batch (one LSTM wave holds 256 rows)");
+  if (cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+  for (auto& ev : b->ev) cudaEventCreate(&ev);
+  const int Hp = e->Hp, Cp = e->Cp, C = m.n_classes;
+  b->rows_per_utt = b->T_cap + 2 * m.n_context + 1;
+  const size_t M_cap = (size_t)b->T_cap * B_cap;
+  bool ok = true;
+  ok &= cudaMallocHost((void**)&b->h_pcm, (size_t)B_cap * b->S_cap * 2) == cudaSuccess;
+  ok &= cudaMallocHost((void**)&b->h_nsamples, 4ull * B_cap) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_pcm, (size_t)B_cap * b->S_cap * 2 + 1024) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_nsamples, 4ull * B_cap) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_feat, (size_t)B_cap * b->rows_per_utt * 64 + 4096) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_feat32, (size_t)B_cap * b->T_cap * m.n_input * 4) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_act_a, (M_cap + 128) * Hp * 2) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_act_b, (M_cap + 128) * Hp * 2) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_xw, (M_cap + 128) * 4ull * Cp * 4) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_hall, (M_cap + B_cap + 256) * Cp * 2) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_c, (size_t)B_cap * Cp * 4) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_h, (size_t)B_cap * Cp * 4) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_barrier, 64) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_probs, (size_t)B_cap * b->T_cap * C * 4) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_win, (size_t)(b->T_cap + 1) * m.win_len * 2) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_jobs, sizeof(sttmfcc::FrameJob) * (b->T_cap + 1)) == cudaSuccess;
+  if (!ok) return fail("device allocation failed");
+  cudaMemset(b->d_feat, 0, (size_t)B_cap * b->rows_per_utt * 64 + 4096);
+  cudaMemset(b->d_hall, 0, (M_cap + B_cap + 256) * Cp * 2);
+  cudaMemset(b->d_c, 0, (size_t)B_cap * Cp * 4);
+  cudaMemset(b->d_h, 0, (size_t)B_cap * Cp * 4);
+  ok &= make_tmap_2d(&b->tm_act_a, b->d_act_a, M_cap + 128, Hp, Hp, 128);
+  ok &= make_tmap_2d(&b->tm_act_b, b->d_act_b, M_cap + 128, Hp, Hp, 128);
+  ok &= make_tmap_2d(&b->tm_hall, b->d_hall, M_cap + B_cap + 256, Cp, Cp, 128);
+  if (!ok) return fail("tensor map creation failed");
+  if (alloc_slots(b) != 0) return fail("decoder slot allocation failed");
+  return b;
+}
+
+void batch_destroy(Batch* b) {
+  if (!b) return;
+  if (b->st) cudaStreamSynchronize(b->st);
+  for (void* p : {(void*)b->d_pcm, (void*)b->d_nsamples, (void*)b->d_feat, (void*)b->d_feat32, (void*)b->d_act_a,
+                  (void*)b->d_act_b, (void*)b->d_xw, (void*)b->d_hall, (void*)b->d_c, (void*)b->d_h, (void*)b->d_barrier,
+                  (void*)b->d_probs, (void*)b->d_win, (void*)b->d_jobs, (void*)b->d_slot_mem, (void*)b->d_slots,
+                  (void*)b->d_inputs, (void*)b->d_finals, (void*)b->d_out_mem, (void*)b->d_winmat})
+    if (p) cudaFree(p);
+  if (b->h_pcm) cudaFreeHost(b->h_pcm);
+  if (b->h_nsamples) cudaFreeHost(b->h_nsamples);
+  if (b->h_out_mem) cudaFreeHost(b->h_out_mem);
+  if (b->st) {
+    for (auto& ev : b->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(b->st);
+  }
+  delete b;
+}
+
+int batch_upload(Batch* b, const int16_t* const* pcm, const unsigned* n_samples, int B) {
+  if (B < 1 || B > b->B_cap) return -1;
+  const auto& m = b->e->hm;
+  b->B = B;
+  b->T_max = 0;
+  for (int u = 0; u < B; ++u) {
+    if ((int)n_samples[u] > b->S_cap) return -2;
+    b->h_nsamples[u] = (int)n_samples[u];
+    memcpy(b->h_pcm + (size_t)u * b->S_cap, pcm[u], (size_t)n_samples[u] * 2);
+    b->T[u] = frames_for((int)n_samples[u], m.win_len, m.win_step);
+    b->T_max = std::max(b->T_max, b->T[u]);
+  }
+  cudaEventRecord(b->ev[0], b->st);
+  // one strided copy when every utterance has the same length, else per utterance
+  bool same = true;
+  for (int u = 1; u < B; ++u) same &= n_samples[u] == n_samples[0];
+  if (same) {
+    CUDA_OK(cudaMemcpy2DAsync(b->d_pcm, (size_t)b->S_cap * 2, b->h_pcm, (size_t)b->S_cap * 2, (size_t)n_samples[0] * 2, B,
+                              cudaMemcpyHostToDevice, b->st));
+  } else {
+    for (int u = 0; u < B; ++u)
+      CUDA_OK(cudaMemcpyAsync(b->d_pcm + (size_t)u * b->S_cap, b->h_pcm + (size_t)u * b->S_cap, (size_t)n_samples[u] * 2,
+                              cudaMemcpyHostToDevice, b->st));
+  }
+  CUDA_OK(cudaMemcpyAsync(b->d_nsamples, b->h_nsamples, 4ull * B, cudaMemcpyHostToDevice, b->st));
+  cudaEventRecord(b->ev[1], b->st);
+  CUDA_OK(cudaStreamSynchronize(b->st));
+  cudaEventElapsedTime(&b->times.h2d, b->ev[0], b->ev[1]);
+  return 0;
+}
+
+namespace {
+
+// dense 1..3 -> xw -> LSTM -> dense 5,6 + softmax for rows (T timesteps x B utterances); features already in d_feat.
+// probs are written at [b, out_t_offset + t].  LSTM initial state = (d_c, block 0 of d_hall); final state -> d_c, d_h.
+int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
+  Engine* e = b->e;
+  const auto& m = e->hm;
+  const int Hp = e->Hp, Cp = e->Cp;
+  const int M = T * B;
+  cudaStream_t st = b->st;
+  // ---- layer 1 through the overlapping-window TMA view
+  int b_box = 1;
+  while (b_box < B && b_box < 128) b_box <<= 1;
+  const int t_box = 128 / b_box;
+  CUtensorMap tm_feat;
+  static bool use_overlap_view = true;
+  if (use_overlap_view) {
+    uint64_t dims[3] = {(uint64_t)e->K1, (uint64_t)(b->rows_per_utt - 2 * m.n_context), (uint64_t)b->B_cap};
+    uint64_t strides[2] = {64, (uint64_t)b->rows_per_utt * 64};
+    uint32_t box[3] = {64, (uint32_t)t_box, (uint32_t)b_box};
+    if (!make_tmap(&tm_feat, b->d_feat, 3, dims, strides, box)) {
+      fprintf(stderr, "[stt_b200] overlapping-row tensor map rejected; using the gathered window matrix\n");
+      use_overlap_view = false;
+    }
+  }
+  sttgemm::GemmParams p{};
+  p.relu_clip = m.relu_clip;
+  p.B = B; p.T = T; p.b_box = b_box; p.t_box = t_box;
+  if (time_it) cudaEventRecord(b->ev[3], st);
+  p.M = M; p.N = Hp; p.K = round_up(e->K1, 64); p.bias = e->b1; p.out = b->d_act_a;
+  if (use_overlap_view) {
+    if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kWindows3D>(tm_feat, e->tm_w1, p, e->num_sms, st)) return -1;
+  } else {
+    const int K1p = round_up(e->K1, 64);
+    if (!b->d_winmat) {
+      const size_t rows = (size_t)b->T_cap * b->B_cap + 128;
+      CUDA_OK(cudaMalloc((void**)&b->d_winmat, rows * K1p * 2));
+      CUDA_OK(cudaMemset(b->d_winmat, 0, rows * K1p * 2));
+      if (!make_tmap_2d(&b->tm_winmat, b->d_winmat, rows, K1p, K1p, 128)) return -1;
+    }
+    gather_windows_kernel<<<M, 128, 0, st>>>(b->d_feat, b->d_winmat, B, T, b->rows_per_utt, e->K1, K1p);
+    CUDA_OK(cudaGetLastError());
+    if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_winmat, e->tm_w1, p, e->num_sms, st)) return -1;
+  }
+  p.K = Hp; p.bias = e->b2; p.out = b->d_act_b;
+  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_a, e->tm_w2, p, e->num_sms, st)) return -1;
+  p.bias = e->b3; p.out = b->d_act_a;
+  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_b, e->tm_w3, p, e->num_sms, st)) return -1;
+  if (time_it) cudaEventRecord(b->ev[4], st);
+  // ---- hoisted input half of the LSTM matmul (+ bias)
+  p.N = 4 * Cp; p.K = Hp; p.bias = e->bx; p.out = b->d_xw;
+  if (launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(b->tm_act_a, e->tm_wx, p, e->num_sms, st)) return -1;
+  if (time_it) cudaEventRecord(b->ev[5], st);
+  // ---- recurrence
+  {
+    CUDA_OK(cudaMemsetAsync(b->d_barrier, 0, 4, st));
+    sttlstm::LstmParams lp{};
+    lp.B = B; lp.T = T; lp.n_cell = Cp; lp.xw = b->d_xw; lp.h_all = b->d_hall; lp.c_state = b->d_c; lp.h_state = b->d_h;
+    lp.barrier = b->d_barrier;
+    const int grid = Cp / sttlstm::kCellsPerCta;
+    void* args[] = {(void*)&b->tm_hall, (void*)&e->tm_wh, (void*)&lp};
+    if (B <= 128) {
+      using L = sttlstm::SmemLayout<1, 6>;
+      auto kern = sttlstm::lstm_tc_kernel<1, 6>;
+      CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+      CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(sttlstm::kNumThreads), args, L::kTotal, st));
+    } else {
+      using L = sttlstm::SmemLayout<2, 5>;
+      auto kern = sttlstm::lstm_tc_kernel<2, 5>;
+      CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+      CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(sttlstm::kNumThreads), args, L::kTotal, st));
+    }
+  }
+  if (time_it) cudaEventRecord(b->ev[6], st);
+  // ---- layer 5 (A = h_1..h_T = rows B.. of h_all) and layer 6 + softmax
+  CUtensorMap tm_h_out;
+  if (!make_tmap_2d(&tm_h_out, b->d_hall + (size_t)B * Cp, (uint64_t)M + 128, Cp, Cp, 128)) return -1;
+  p.N = Hp; p.K = Cp; p.bias = e->b5; p.out = b->d_act_b;
+  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(tm_h_out, e->tm_w5, p, e->num_sms, st)) return -1;
+  p.N = 32; p.K = Hp; p.bias = e->b6; p.out = b->d_probs; p.n_valid = m.n_classes;
+  p.out_T_stride = b->T_cap; p.out_t_offset = out_t_offset;
+  if (launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(b->tm_act_b, e->tm_w6, p, e->num_sms, st)) return -1;
+  if (time_it) cudaEventRecord(b->ev[7], st);
+  b->launches += 7;
+  return 0;
+}
+
+}  // namespace
+
+int batch_forward(Batch* b) {
+  Engine* e = b->e;
+  const auto& m = e->hm;
+  if (b->B < 1) return -1;
+  cudaStream_t st = b->st;
+  const int B = b->B, T = b->T_max;
+  cudaEventRecord(b->ev[2], st);
+  // features: zero the padded stream (context zeros + lanes), then one CTA per analysis window
+  CUDA_OK(cudaMemsetAsync(b->d_feat, 0, (size_t)b->B_cap * b->rows_per_utt * 64, st));
+  sttmfcc::BatchJob job{};
+  job.pcm = b->d_pcm; job.n_samples = b->d_nsamples; job.stride = b->S_cap; job.frames_per_utt = b->T_cap;
+  job.out_f32 = b->d_feat32; job.out_f16 = b->d_feat; job.f16_frames_per_utt = b->rows_per_utt;
+  job.f16_row_offset = m.n_context;
+  // grid covers frames_per_utt = T_cap per utterance; blocks beyond an utterance's frame count exit immediately
+  {
+    sttmfcc::BatchJob j2 = job;
+    const int grid = B * b->T_cap;
+    sttmfcc::mfcc_batch_kernel<<<grid, 256, 0, st>>>(e->tables, j2);
+    CUDA_OK(cudaGetLastError());
+    b->launches += 1;
+  }
+  // offline: LSTM starts from zeros (STT_CreateStream, stt.cc:535-536)
+  CUDA_OK(cudaMemsetAsync(b->d_c, 0, (size_t)b->B_cap * e->Cp * 4, st));
+  CUDA_OK(cudaMemsetAsync(b->d_hall, 0, (size_t)b->B_cap * e->Cp * 2, st));
+  if (run_am(b, B, T, 0, true)) return -1;
+  CUDA_OK(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&b->times.mfcc, b->ev[2], b->ev[3]);
+  cudaEventElapsedTime(&b->times.dense123, b->ev[3], b->ev[4]);
+  cudaEventElapsedTime(&b->times.lstm_in, b->ev[4], b->ev[5]);
+  cudaEventElapsedTime(&b->times.lstm, b->ev[5], b->ev[6]);
+  cudaEventElapsedTime(&b->times.dense56, b->ev[6], b->ev[7]);
+  return 0;
+}
+
+namespace {
+
+sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
+  const Engine* e = b->e;
+  sttdec::DecodeParams dp{};
+  dp.n_classes = e->hm.n_classes;
+  dp.beam = beam;
+  dp.space_id = (int)e->hm.space_label;
+  dp.has_scorer = e->has_scorer ? 1 : 0;
+  if (e->has_scorer) dp.scorer = e->scorer_view;
+  return dp;
+}
+
+int decoder_reset(Batch* b, int n_slots) {
+  cudaStream_t st = b->st;
+  // hash tables must start empty
+  for (int u = 0; u < n_slots; ++u)
+    CUDA_OK(cudaMemsetAsync(b->h_slots[u].ht_key, 0, 8ull * (b->h_slots[u].ht_mask + 1), st));
+  const int32_t fst_start = b->e->has_scorer ? (int32_t)b->e->scorer_view.fst_start : 0;
+  sttdec::decoder_init_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b->d_slots, n_slots, fst_start);
+  CUDA_OK(cudaGetLastError());
+  b->launches += 1;
+  return 0;
+}
+
+int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& in, int beam) {
+  cudaStream_t st = b->st;
+  CUDA_OK(cudaMemcpyAsync(b->d_inputs, in.data(), sizeof(sttdec::StepInput) * n_slots, cudaMemcpyHostToDevice, st));
+  const sttdec::DecodeParams dp = make_decode_params(b, beam);
+  constexpr int NT = 512;
+  const size_t dyn = 8ull * b->beam_cap;
+  sttdec::decoder_step_kernel<NT><<<n_slots, NT, dyn, st>>>(b->d_slots, b->d_inputs, dp);
+  CUDA_OK(cudaGetLastError());
+  b->launches += 1;
+  return 0;
+}
+
+int decoder_finalize(Batch* b, int n_slots, int beam, int num_results) {
+  const sttdec::DecodeParams dp = make_decode_params(b, beam);
+  sttdec::decoder_finalize_kernel<256><<<n_slots, 256, 0, b->st>>>(b->d_slots, b->d_finals, dp, num_results);
+  CUDA_OK(cudaGetLastError());
+  b->launches += 1;
+  return 0;
+}
+
+int ensure_results_capacity(Batch* b, int num_results) {
+  if (num_results <= b->max_results) return 0;
+  // re-create output buffers with a larger result count
+  cudaStreamSynchronize(b->st);
+  cudaFree(b->d_out_mem); b->d_out_mem = nullptr;
+  cudaFreeHost(b->h_out_mem); b->h_out_mem = nullptr;
+  cudaFree(b->d_finals); b->d_finals = nullptr;
+  b->max_results = num_results;
+  const int R = b->max_results, Tm = b->dec_T_cap;
+  size_t per = 8;
+  const size_t o_conf = per; per += 8ull * R;
+  const size_t o_nt = per; per += 4ull * R;
+  per = align_up(per, 8);
+  const size_t o_tok = per; per += 4ull * R * Tm;
+  const size_t o_ts = per; per += 4ull * R * Tm;
+  per = align_up(per, 256);
+  b->out_bytes_per_utt = per;
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_out_mem), per * b->B_cap));
+  CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&b->h_out_mem), per * b->B_cap));
+  std::vector<sttdec::FinalOut> fo(b->B_cap);
+  for (int u = 0; u < b->B_cap; ++u) {
+    uint8_t* base = b->d_out_mem + per * u;
+    fo[u].max_results = R; fo[u].max_tokens = Tm;
+    fo[u].n_results = (int*)base; fo[u].confidence = (double*)(base + o_conf); fo[u].n_tokens = (int*)(base + o_nt);
+    fo[u].tokens = (uint32_t*)(base + o_tok); fo[u].timesteps = (uint32_t*)(base + o_ts);
+  }
+  CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_finals), sizeof(sttdec::FinalOut) * b->B_cap));
+  CUDA_OK(cudaMemcpy(b->d_finals, fo.data(), sizeof(sttdec::FinalOut) * b->B_cap, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// parse one utterance's result block (host copy)
+void parse_results(const Batch* b, const uint8_t* base, std::vector<Decoded>* out) {
+  const int R = b->max_results, Tm = b->dec_T_cap;
+  size_t per = 8;
+  const size_t o_conf = per; per += 8ull * R;
+  const size_t o_nt = per; per += 4ull * R;
+  per = align_up(per, 8);
+  const size_t o_tok = per; per += 4ull * R * Tm;
+  const size_t o_ts = per;
+  const int n = *reinterpret_cast<const int*>(base);
+  out->clear();
+  for (int r = 0; r < n; ++r) {
+    Decoded d;
+    d.confidence = reinterpret_cast<const double*>(base + o_conf)[r];
+    const int nt = std::min(reinterpret_cast<const int*>(base + o_nt)[r], Tm);
+    const uint32_t* tok = reinterpret_cast<const uint32_t*>(base + o_tok) + (size_t)r * Tm;
+    const uint32_t* ts = reinterpret_cast<const uint32_t*>(base + o_ts) + (size_t)r * Tm;
+    d.tokens.assign(tok, tok + nt);
+    d.timesteps.assign(ts, ts + nt);
+    out->push_back(std::move(d));
+  }
+}
+
+}  // namespace
+
+int batch_decode(Batch* b, int beam, int num_results) {
+  if (b->B < 1 || beam < 1 || beam > b->beam_cap) return -1;
+  if (ensure_results_capacity(b, num_results)) return -1;
+  b->cur_beam = beam;
+  b->cur_results = num_results;
+  cudaStream_t st = b->st;
+  cudaEventRecord(b->ev[8], st);
+  if (decoder_reset(b, b->B)) return -1;
+  std::vector<sttdec::StepInput> in(b->B);
+  for (int u = 0; u < b->B; ++u) {
+    in[u].probs = b->d_probs + (size_t)u * b->T_cap * b->e->hm.n_classes;
+    in[u].n_steps = b->T[u];
+  }
+  if (decoder_steps(b, b->B, in, beam)) return -1;
+  if (decoder_finalize(b, b->B, beam, num_results)) return -1;
+  cudaEventRecord(b->ev[9], st);
+  CUDA_OK(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&b->times.decode, b->ev[8], b->ev[9]);
+  return 0;
+}
+
+int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out) {
+  cudaStream_t st = b->st;
+  cudaEventRecord(b->ev[10], st);
+  // header + first result rows are small; copy only what the results can occupy: [0, o_ts + used)
+  CUDA_OK(cudaMemcpyAsync(b->h_out_mem, b->d_out_mem, b->out_bytes_per_utt * b->B, cudaMemcpyDeviceToHost, st));
+  cudaEventRecord(b->ev[11], st);
+  CUDA_OK(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&b->times.d2h, b->ev[10], b->ev[11]);
+  // overflow check: a decoder that ran out of arena space must fail loudly
+  for (int u = 0; u < b->B; ++u) {
+    uint32_t sc[8];
+    CUDA_OK(cudaMemcpy(sc, b->h_slots[u].scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+    if (sc[6]) {
+      fprintf(stderr, "[stt_b200] decoder capacity exceeded for utterance %d\n", u);
+      return -3;
+    }
+  }
+  out->resize(b->B);
+  for (int u = 0; u < b->B; ++u) parse_results(b, b->h_out_mem + b->out_bytes_per_utt * u, &(*out)[u]);
+  return 0;
+}
+
+int batch_copy_features(Batch* b, int utt, float* out) {
+  if (utt < 0 || utt >= b->B) return -1;
+  const int ni = b->e->hm.n_input;
+  CUDA_OK(cudaMemcpy(out, b->d_feat32 + (size_t)utt * b->T_cap * ni, (size_t)b->T[utt] * ni * 4, cudaMemcpyDeviceToHost));
+  return b->T[utt];
+}
+int batch_copy_probs(Batch* b, int utt, float* out) {
+  if (utt < 0 || utt >= b->B) return -1;
+  const int C = b->e->hm.n_classes;
+  CUDA_OK(cudaMemcpy(out, b->d_probs + (size_t)utt * b->T_cap * C, (size_t)b->T[utt] * C * 4, cudaMemcpyDeviceToHost));
+  return b->T[utt];
+}
+int batch_set_probs(Batch* b, const float* probs, const int* T, int B, int T_stride) {
+  if (B < 1 || B > b->B_cap) return -1;
+  const int C = b->e->hm.n_classes;
+  b->B = B;
+  b->T_max = 0;
+  for (int u = 0; u < B; ++u) {
+    if (T[u] > b->T_cap) return -2;
+    b->T[u] = T[u];
+    b->T_max = std::max(b->T_max, T[u]);
+    CUDA_OK(cudaMemcpy(b->d_probs + (size_t)u * b->T_cap * C, probs + (size_t)u * T_stride * C, (size_t)T[u] * C * 4,
+                       cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+// ====================================================================================== streaming (B == 1)
+int batch_stream_reset(Batch* b, int beam) {
+  if (beam < 1 || beam > b->beam_cap) return -1;
+  Engine* e = b->e;
+  b->B = 1;
+  b->cur_beam = beam;
+  b->stream_frames = 0;
+  cudaStream_t st = b->st;
+  CUDA_OK(cudaMemsetAsync(b->d_feat, 0, (size_t)b->rows_per_utt * 64, st));
+  CUDA_OK(cudaMemsetAsync(b->d_c, 0, (size_t)e->Cp * 4, st));
+  CUDA_OK(cudaMemsetAsync(b->d_h, 0, (size_t)e->Cp * 4, st));
+  if (decoder_reset(b, 1)) return -1;
+  // mfcc_buffer_ starts with n_context literal-zero frames (stt.cc:533)
+  b->stream_frames = e->hm.n_context;
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int batch_stream_push_windows(Batch* b, const int16_t* windows, const int* n_valid, int n_windows, int n_zero_frames) {
+  Engine* e = b->e;
+  const auto& m = e->hm;
+  if (b->stream_frames + n_windows + n_zero_frames > b->rows_per_utt) return -2;
+  cudaStream_t st = b->st;
+  if (n_windows > 0) {
+    if (n_windows > b->T_cap + 1) return -2;
+    CUDA_OK(cudaMemcpyAsync(b->d_win, windows, (size_t)n_windows * m.win_len * 2, cudaMemcpyHostToDevice, st));
+    std::vector<sttmfcc::FrameJob> jobs(n_windows);
+    for (int i = 0; i < n_windows; ++i) {
+      jobs[i].pcm = b->d_win + (size_t)i * m.win_len;
+      jobs[i].n_valid = n_valid[i];
+      jobs[i].out_f32 = nullptr;
+      jobs[i].out_f16 = b->d_feat + (size_t)(b->stream_frames + i) * sttmfcc::kFeatLanes;
+    }
+    CUDA_OK(cudaMemcpyAsync(b->d_jobs, jobs.data(), sizeof(sttmfcc::FrameJob) * n_windows, cudaMemcpyHostToDevice, st));
+    sttmfcc::mfcc_jobs_kernel<<<n_windows, 256, 0, st>>>(e->tables, b->d_jobs);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(st));  // `jobs` is a host temporary
+    b->launches += 1;
+    b->stream_frames += n_windows;
+  }
+  if (n_zero_frames > 0) {
+    CUDA_OK(cudaMemsetAsync(b->d_feat + (size_t)b->stream_frames * sttmfcc::kFeatLanes, 0, (size_t)n_zero_frames * 64, st));
+    b->stream_frames += n_zero_frames;
+  }
+  return 0;
+}
+
+int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_probs) {
+  (void)keep_last_probs;
+  Engine* e = b->e;
+  const auto& m = e->hm;
+  const int need = n_timesteps + 2 * (int)m.n_context;
+  if (n_timesteps < 1 || n_timesteps > b->T_cap || b->stream_frames < need) return -2;
+  cudaStream_t st = b->st;
+  // carried LSTM state: h (fp32) -> block 0 of h_all (fp16); c stays in d_c
+  f32_to_f16_kernel<<<(e->Cp + 255) / 256, 256, 0, st>>>(b->d_h, b->d_hall, (size_t)e->Cp);
+  b->launches += 1;
+  if (run_am(b, 1, n_timesteps, 0, false)) return -1;
+  // DecoderState::next on the new rows
+  std::vector<sttdec::StepInput> in(1);
+  in[0].probs = b->d_probs;
+  in[0].n_steps = n_timesteps;
+  if (decoder_steps(b, 1, in, b->cur_beam)) return -1;
+  b->last_run_T = n_timesteps;
+  // consume the timesteps: slide the frame stream left
+  const int keep = b->stream_frames - n_timesteps;
+  shift_frames_kernel<<<1, 32, 0, st>>>(b->d_feat, keep, n_timesteps, sttmfcc::kFeatLanes, b->stream_frames);
+  b->launches += 1;
+  b->stream_frames = keep;
+  if (n_pad_rows > 0) {
+    // The reference zero-pads a partial batch to n_steps rows and the LSTM state advances through the padding
+    // (tflitemodelstate.cc:381; SURVEY 3.4 "trashing").  Reproduce by running the AM on all-zero windows with the
+    // outputs discarded: a scratch all-zero feature stream sits after the live frames.
+    // Zero windows = frames beyond stream_frames, which are zero by construction (shift kernel / reset).
+    // We temporarily view the stream starting at the first all-zero region.
+    const int zero_start = b->stream_frames;  // frames [zero_start, rows_per_utt) are zero
+    if (zero_start + n_pad_rows + 2 * (int)m.n_context > b->rows_per_utt) return -2;
+    f32_to_f16_kernel<<<(e->Cp + 255) / 256, 256, 0, st>>>(b->d_h, b->d_hall, (size_t)e->Cp);
+    b->launches += 1;
+    __half* saved = b->d_feat;
+    b->d_feat = saved + (size_t)zero_start * sttmfcc::kFeatLanes;
+    const int saved_rows = b->rows_per_utt;
+    b->rows_per_utt = saved_rows - zero_start;
+    // probs of these rows land after the real ones and are never read
+    int rc = run_am(b, 1, n_pad_rows, n_timesteps, false);
+    b->d_feat = saved;
+    b->rows_per_utt = saved_rows;
+    if (rc) return -1;
+  }
+  CUDA_OK(cudaStreamSynchronize(st));
+  uint32_t sc[8];
+  CUDA_OK(cudaMemcpy(sc, b->h_slots[0].scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+  if (sc[6]) {
+    fprintf(stderr, "[stt_b200] stream decoder capacity exceeded (raise STT_B200_STREAM_MAX_SECONDS)\n");
+    return -3;
+  }
+  return 0;
+}
+
+int batch_stream_decode(Batch* b, int num_results, std::vector<Decoded>* out) {
+  if (ensure_results_capacity(b, num_results)) return -1;
+  if (decoder_finalize(b, 1, b->cur_beam, num_results)) return -1;
+  CUDA_OK(cudaMemcpyAsync(b->h_out_mem, b->d_out_mem, b->out_bytes_per_utt, cudaMemcpyDeviceToHost, b->st));
+  CUDA_OK(cudaStreamSynchronize(b->st));
+  parse_results(b, b->h_out_mem, out);
+  return 0;
+}
+
+int batch_stream_frames(const Batch* b) { return b->stream_frames; }
+
+int batch_stream_last_probs(Batch* b, std::vector<double>* out, int* n_rows) {
+  const int C = b->e->hm.n_classes;
+  std::vector<float> tmp((size_t)b->last_run_T * C);
+  CUDA_OK(cudaMemcpy(tmp.data(), b->d_probs, tmp.size() * 4, cudaMemcpyDeviceToHost));
+  out->assign(tmp.begin(), tmp.end());
+  *n_rows = b->last_run_T;
+  return 0;
+}
+
+// ====================================================================================== GEMM unit-test hook
+int debug_gemm(int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16, const float* bias, int epi,
+               float relu_clip, void* out, float* ms) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int BN = (epi == sttgemm::kEpiSoftmaxF32) ? 32 : 256;
+  if (N % BN != 0 || K % 8 != 0) return -2;
+  __half *dA, *dW;
+  float* dB;
+  void* dO;
+  const size_t out_elem = (epi == sttgemm::kEpiClipReluF16) ? 2 : 4;
+  const int n_valid = (epi == sttgemm::kEpiSoftmaxF32) ? std::min(N, 29) : N;
+  const size_t out_count = (epi == sttgemm::kEpiSoftmaxF32) ? (size_t)M * n_valid : (size_t)M * N;
+  CUDA_OK(cudaMalloc((void**)&dA, (size_t)(M + 128) * K * 2));
+  CUDA_OK(cudaMalloc((void**)&dW, (size_t)N * K * 2));
+  CUDA_OK(cudaMalloc((void**)&dB, (size_t)N * 4));
+  CUDA_OK(cudaMalloc(&dO, out_count * out_elem));
+  CUDA_OK(cudaMemset(dA, 0, (size_t)(M + 128) * K * 2));
+  CUDA_OK(cudaMemcpy(dA, a_f16, (size_t)M * K * 2, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dW, w_f16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+  CUtensorMap ta, tb;
+  if (!make_tmap_2d(&ta, dA, M + 128, K, K, 128) || !make_tmap_2d(&tb, dW, N, K, K, BN)) return -1;
+  sttgemm::GemmParams p{};
+  p.M = M; p.N = N; p.K = round_up(K, 64); p.bias = dB; p.out = dO; p.relu_clip = relu_clip; p.n_valid = n_valid;
+  p.B = 1; p.T = M; p.out_T_stride = M; p.out_t_offset = 0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int rc = 0;
+  for (int it = 0; it < 2 && rc == 0; ++it) {  // second run is the timed one
+    cudaEventRecord(e0, 0);
+    if (epi == sttgemm::kEpiClipReluF16) rc = launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(ta, tb, p, sms, 0);
+    else if (epi == sttgemm::kEpiBiasF32) rc = launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(ta, tb, p, sms, 0);
+    else rc = launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(ta, tb, p, sms, 0);
+    cudaEventRecord(e1, 0);
+    if (cudaDeviceSynchronize() != cudaSuccess) rc = -1;
+  }
+  if (rc == 0) {
+    if (ms) cudaEventElapsedTime(ms, e0, e1);
+    if (cudaMemcpy(out, dO, out_count * out_elem, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dO);
+  return rc;
+}
+
+}  // namespace stteng

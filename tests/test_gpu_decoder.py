@@ -1,0 +1,131 @@
+"""GPU beam search (stt_b200/csrc/decoder.cuh) vs the GENUINE reference decoder (oracle/_ref/libref_decoder.so) on
+identical float32 probabilities: token ids, timesteps and confidence of the top results must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SCORER
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(small_model, beam, scorer=True):
+    from stt_b200 import Model
+    path, _ = small_model
+    m = Model(path)
+    m.setBeamWidth(beam)
+    if scorer:
+        m.enableExternalScorer(SCORER)
+    return m
+
+
+def _compare(gpu_results, ref_results, what, conf_exact=True):
+    assert len(gpu_results) == len(ref_results), what
+    for r, ((gc, gt, gts), (rc, rt, rts)) in enumerate(zip(gpu_results, ref_results)):
+        assert list(gt) == list(rt), "%s: tokens of result %d differ" % (what, r)
+        assert list(gts) == list(rts), "%s: timesteps of result %d differ" % (what, r)
+        if conf_exact:
+            assert gc == rc, "%s: confidence of result %d differs: %r vs %r" % (what, r, gc, rc)
+        else:
+            assert abs(gc - rc) <= 1e-4 * max(1.0, abs(rc))
+
+
+@pytest.mark.parametrize("beam", [1, 8, 100, 500])
+@pytest.mark.parametrize("T", [50, 200])
+def test_decoder_with_scorer_matches_reference(ref_decoder, small_model, vocab_words, english, beam, T):
+    from stt_b200 import synth
+    o = ref_decoder
+    alpha = o.RefAlphabet(english)
+    sc = o.RefScorer(SCORER, alpha)
+    m = _model(small_model, beam)
+    B = 6
+    probs = np.stack([synth.make_ctc_probs(vocab_words, T, utt=100 * beam + u) for u in range(B)])
+    b = m.createBatch(B, T * 320)
+    b.set_probs(probs, [T] * B)
+    b.decode(num_results=3)
+    b.fetch()
+    for u in range(B):
+        ref = o.ref_decode(probs[u], alpha, beam, sc, num_results=3)
+        _compare(b.results(u), ref, "beam=%d T=%d utt=%d" % (beam, T, u))
+
+
+@pytest.mark.parametrize("beam", [4, 64])
+def test_decoder_without_scorer_matches_reference(ref_decoder, small_model, vocab_words, english, beam):
+    from stt_b200 import synth
+    o = ref_decoder
+    alpha = o.RefAlphabet(english)
+    m = _model(small_model, beam, scorer=False)
+    T, B = 60, 4
+    probs = np.stack([synth.make_ctc_probs(vocab_words, T, utt=900 + u) for u in range(B)])
+    b = m.createBatch(B, T * 320)
+    b.set_probs(probs, [T] * B)
+    b.decode(num_results=2)
+    b.fetch()
+    for u in range(B):
+        ref = o.ref_decode(probs[u], alpha, beam, None, num_results=2)
+        _compare(b.results(u), ref, "noscorer beam=%d utt=%d" % (beam, u))
+
+
+def test_decoder_edge_cases(ref_decoder, small_model, vocab_words, english):
+    """All-blank input (gate never opens), near-uniform softmax, ragged lengths, single frame."""
+    from stt_b200 import synth
+    o = ref_decoder
+    alpha = o.RefAlphabet(english)
+    sc = o.RefScorer(SCORER, alpha)
+    beam = 50
+    m = _model(small_model, beam)
+    T = 40
+    C = 29
+    rng = np.random.default_rng(5)
+    blank = np.full((T, C), 1e-5, np.float32)
+    blank[:, 28] = 1.0
+    blank /= blank.sum(1, keepdims=True)
+    uniform = rng.dirichlet(np.ones(C) * 50, size=T).astype(np.float32)
+    normal = synth.make_ctc_probs(vocab_words, T, utt=77)
+    probs = np.stack([blank, uniform, normal, normal])
+    lens = [T, T, 1, 17]
+    b = m.createBatch(4, T * 320)
+    b.set_probs(probs, lens)
+    b.decode(num_results=2)
+    b.fetch()
+    for u in range(4):
+        ref = o.ref_decode(probs[u][:lens[u]], alpha, beam, sc, num_results=2)
+        _compare(b.results(u), ref, "edge utt=%d" % u)
+
+
+def test_decoder_alpha_beta_sweep(ref_decoder, small_model, vocab_words, english):
+    """config 5 of BASELINE.json in miniature: lm_alpha / lm_beta grid, parity at every point."""
+    from stt_b200 import synth
+    o = ref_decoder
+    alpha = o.RefAlphabet(english)
+    sc = o.RefScorer(SCORER, alpha)
+    m = _model(small_model, 100)
+    T = 120
+    probs = np.stack([synth.make_ctc_probs(vocab_words, T, utt=4242)])
+    for a in (0.5, 0.931289039105002, 1.5):
+        for be in (0.5, 1.1834137581510284, 2.0):
+            sc.set_alpha_beta(a, be)
+            m.setScorerAlphaBeta(a, be)
+            b = m.createBatch(1, T * 320)
+            b.set_probs(probs, [T])
+            b.decode(num_results=1)
+            b.fetch()
+            _compare(b.results(0), o.ref_decode(probs[0], alpha, 100, sc), "alpha=%g beta=%g" % (a, be))
+
+
+def test_decoder_against_committed_golden(small_model):
+    """Golden vectors produced by the reference decoder in the build container (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, "decoder_golden.npz"), allow_pickle=True)
+    m = _model(small_model, int(g["beam"]))
+    probs = g["probs"]
+    B, T, _ = probs.shape
+    b = m.createBatch(B, T * 320)
+    b.set_probs(probs, [T] * B)
+    b.decode(num_results=1)
+    b.fetch()
+    for u in range(B):
+        conf, tok, ts = b.results(u)[0]
+        assert list(tok) == list(g["tokens"][u])
+        assert list(ts) == list(g["timesteps"][u])
+        assert conf == float(g["confidence"][u])
