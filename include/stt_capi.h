@@ -168,6 +168,8 @@ STT_EXPORT int STTX_BatchTokens(STTX_Batch* b, unsigned int u, unsigned int r, u
 STT_EXPORT int STTX_BatchFetch(STTX_Batch* b);                         /* device -> host copy of the decode results */
 STT_EXPORT int STTX_BatchGetTimings(STTX_Batch* b, STTX_Timings* out);
 STT_EXPORT long long STTX_BatchKernelLaunches(STTX_Batch* b);
+/* instrumentation: words scored by the LM / LM calls in the last STTX_BatchDecode (decoder roofline's Q) */
+STT_EXPORT int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls);
 /* test hooks */
 STT_EXPORT int STTX_BatchTimesteps(STTX_Batch* b, unsigned int u);
 STT_EXPORT int STTX_BatchCopyFeatures(STTX_Batch* b, unsigned int u, float* out);  /* [T, n_input] */

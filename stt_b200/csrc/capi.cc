@@ -553,6 +553,9 @@ int STTX_BatchGetTimings(STTX_Batch* b, STTX_Timings* out) {
   return STT_ERR_OK;
 }
 long long STTX_BatchKernelLaunches(STTX_Batch* b) { return stteng::batch_kernel_launches(b->dev); }
+int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls) {
+  return stteng::batch_lm_stats(b->dev, words_scored, lm_calls) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
+}
 int STTX_BatchTimesteps(STTX_Batch* b, unsigned int u) { return stteng::batch_T(b->dev, (int)u); }
 int STTX_BatchCopyFeatures(STTX_Batch* b, unsigned int u, float* out) { return stteng::batch_copy_features(b->dev, (int)u, out); }
 int STTX_BatchCopyProbs(STTX_Batch* b, unsigned int u, float* out) { return stteng::batch_copy_probs(b->dev, (int)u, out); }

@@ -71,7 +71,7 @@ struct Slot {
   float* lm_term;        // [beam_cap] (float)((cond_prob + boost) * alpha) for "prefix i + space"
   uint32_t* lm_word;     // [beam_cap] vocab id of the word completed by that space
   // scalars (persist across launches for streaming)
-  uint32_t* scalars;     // [8]: 0 n_live, 1 live_sel, 2 arena_count, 3 ts_count, 4 abs_time_step, 5 start_expanding, 6 overflow
+  uint32_t* scalars;     // [16]: 7 LM words scored, 8 LM calls; 0 n_live, 1 live_sel, 2 arena_count, 3 ts_count, 4 abs_time_step, 5 start_expanding, 6 overflow
   uint32_t arena_cap, ts_cap, beam_cap, cand_cap;
 };
 
@@ -132,7 +132,8 @@ __device__ __forceinline__ bool visits_before(float sx, uint32_t cx, uint32_t ix
 // Scorer::make_ngram + get_log_cond_prob for "prefix `node` followed by a space" (word mode).
 // Returns (float)(cond_prob * alpha) exactly as ctc_beam_search_decoder.cpp:239 computes it (hot-word boost = 0)
 // and the vocabulary id of the completed word.
-__device__ float lm_space_term(const Slot& s, const sttscorer::ScorerView& v, uint32_t node, uint32_t* word_out) {
+__device__ float lm_space_term(const Slot& s, const sttscorer::ScorerView& v, uint32_t node, uint32_t* word_out,
+                               uint32_t* n_words_out = nullptr) {
   uint32_t ids_rev[sttscorer::kMaxOrder];
   int n = 0;
   uint32_t first_word = 0;
@@ -169,6 +170,7 @@ __device__ float lm_space_term(const Slot& s, const sttscorer::ScorerView& v, ui
     cur = s.parent[stop];
   }
   *word_out = first_word;
+  if (n_words_out) *n_words_out = (uint32_t)n;
   uint32_t ids[sttscorer::kMaxOrder];
   for (int i = 0; i < n; ++i) ids[i] = ids_rev[n - 1 - i];
   const bool bos = n < order;
@@ -210,6 +212,7 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start)
   s.scalars[5] = 0;  // start_expanding
   s.scalars[6] = 0;  // overflow flag
   s.scalars[7] = 0;
+  s.scalars[8] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ step kernel
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   uint32_t abs_t = s.scalars[4];
   uint32_t start_expanding = s.scalars[5];
   uint32_t overflow = s.scalars[6];
+  if (threadIdx.x == 0) { s_u[6] = 0; s_u[7] = 0; }
 
   for (int step = 0; step < in.n_steps; ++step, ++abs_t) {
     const float* prob = in.probs + (size_t)step * C;
@@ -341,9 +345,11 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         const uint32_t q = base + (uint32_t)(l * NW + w);
         if (q < n_lm) {
           const uint32_t i = s_lmq[q];
-          uint32_t wid;
-          s.lm_term[i] = lm_space_term(s, sv, L_node[i], &wid);
+          uint32_t wid, nw;
+          s.lm_term[i] = lm_space_term(s, sv, L_node[i], &wid, &nw);
           s.lm_word[i] = wid;
+          atomicAdd(&s_u[6], nw);  // instrumentation: words scored (Q of SURVEY 8d's decoder roofline)
+          atomicAdd(&s_u[7], 1u);  // LM calls
         }
       }
       __syncthreads();
@@ -664,6 +670,8 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     s.scalars[4] = abs_t;
     s.scalars[5] = start_expanding;
     s.scalars[6] = overflow;
+    s.scalars[7] += s_u[6];   // words scored by the LM in this launch
+    s.scalars[8] += s_u[7];   // LM calls
   }
 }
 

@@ -856,6 +856,18 @@ int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out) {
   return 0;
 }
 
+int batch_lm_stats(Batch* b, unsigned long long* words, unsigned long long* calls) {
+  *words = 0;
+  *calls = 0;
+  for (int u = 0; u < b->B; ++u) {
+    uint32_t sc[16];
+    CUDA_OK(cudaMemcpy(sc, b->h_slots[u].scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+    *words += sc[7];
+    *calls += sc[8];
+  }
+  return 0;
+}
+
 int batch_copy_features(Batch* b, int utt, float* out) {
   if (utt < 0 || utt >= b->B) return -1;
   const int ni = b->e->hm.n_input;

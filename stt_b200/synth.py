@@ -45,6 +45,86 @@ def make_weights(n_hidden=2048, n_input=26, n_context=9, n_classes=29, seed=1234
     return w
 
 
+def _np_forward_h5(w, mfcc, n_context=9, relu_clip=20.0):
+    """numpy restatement of the layer stack up to layer 5 (deepspeech_model.py:204-251); used only to calibrate the
+    synthetic output layer below."""
+    F, ni = mfcc.shape
+    pad = np.zeros((n_context, ni), np.float32)
+    seq = np.concatenate([pad, mfcc.astype(np.float32), pad])
+    x = np.stack([seq[t:t + 2 * n_context + 1].reshape(-1) for t in range(F)])
+    relu = lambda v: np.clip(v, 0.0, relu_clip)
+    a = relu(relu(relu(x @ w["w1"] + w["b1"]) @ w["w2"] + w["b2"]) @ w["w3"] + w["b3"])
+    C = w["lstm_bias"].size // 4
+    c = np.zeros(C, np.float32)
+    h = np.zeros(C, np.float32)
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    hs = []
+    for t in range(F):
+        g = np.concatenate([a[t], h]) @ w["lstm_kernel"] + w["lstm_bias"]
+        c = sig(g[2 * C:3 * C]) * c + sig(g[:C]) * np.tanh(g[C:2 * C])
+        h = sig(g[3 * C:]) * np.tanh(c)
+        hs.append(h)
+    return relu(np.stack(hs).astype(np.float32) @ w["w5"] + w["b5"])
+
+
+def np_mfcc(pcm, sample_rate=16000, win_len=512, win_step=320, n_dct=26, n_channels=40, lower=20.0):
+    """numpy MFCC of every analysis window incl. the zero-padded flush window (same recipe as SURVEY appendix B);
+    only used to calibrate synthetic weights -- the tests use the oracle restatement, not this."""
+    pcm = np.asarray(pcm, np.int16)
+    F = n_timesteps(pcm.size, win_len, win_step)
+    x = np.zeros((F - 1) * win_step + win_len, np.float64)
+    x[:pcm.size] = pcm.astype(np.float32) * np.float32(1.0 / 32768.0)
+    hann = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(win_len) / win_len)
+    frames = np.stack([x[f * win_step:f * win_step + win_len] * hann for f in range(F)])
+    fft = 1
+    while fft < win_len:
+        fft *= 2
+    power = (np.abs(np.fft.rfft(frames, fft, axis=1)) ** 2).astype(np.float32).astype(np.float64)
+    n_bins = fft // 2 + 1
+    upper = sample_rate / 2.0
+    mel = lambda f: 1127.0 * np.log1p(f / 700.0)
+    centers = mel(lower) + (mel(upper) - mel(lower)) / (n_channels + 1) * (np.arange(n_channels + 1) + 1)
+    hz = 0.5 * sample_rate / (n_bins - 1)
+    start, end = int(1.5 + lower / hz), int(upper / hz)
+    out = np.zeros((F, n_channels))
+    spec = np.sqrt(power)
+    ch = 0
+    for i in range(start, min(end, n_bins - 1) + 1):
+        m = mel(i * hz)
+        while ch < n_channels and centers[ch] < m:
+            ch += 1
+        c = ch - 1
+        wgt = (centers[c + 1] - m) / (centers[c + 1] - centers[c]) if c >= 0 else (centers[0] - m) / (centers[0] - mel(lower))
+        if c >= 0:
+            out[:, c] += spec[:, i] * wgt
+        if c + 1 < n_channels:
+            out[:, c + 1] += spec[:, i] * (1.0 - wgt)
+    logmel = np.log(np.maximum(out, 1e-12))
+    dct = np.sqrt(2.0 / n_channels) * np.cos(np.arange(n_dct)[:, None] * (np.pi / n_channels) * (np.arange(n_channels)[None, :] + 0.5))
+    return (logmel @ dct.T).astype(np.float32)
+
+
+def bench_weights(n_hidden=2048, seed=1234, scale=200.0, blank_bias=18.0):
+    """The benchmark / smoke-test acoustic model: random init (make_weights) + CTC-like output layer calibrated on a
+    fixed 4 s synthetic clip (make_ctc_like).  Deterministic in (n_hidden, seed)."""
+    w = make_weights(n_hidden=n_hidden, seed=seed)
+    return make_ctc_like(w, np_mfcc(make_pcm(64000, utt=777)), scale=scale, blank_bias=blank_bias)
+
+
+def make_ctc_like(weights, mfcc_calib, scale=200.0, blank_bias=18.0):
+    """Random-initialised networks emit a near-uniform, almost time-invariant softmax (max p ~ 0.04), which no CTC
+    decoder ever sees in practice.  Keep every weight random but re-initialise the OUTPUT layer so the softmax is
+    peaky, blank-favouring and follows the input: w6 <- scale * w6, b6 <- -mean_t(h5) @ w6 (centres the logits on a
+    calibration clip) with +blank_bias on the CTC blank.  The reference CPU arm runs the same weights."""
+    w = dict(weights)
+    h5 = _np_forward_h5(w, mfcc_calib)
+    w6 = (w["w6"] * scale).astype(np.float32)
+    b6 = -(h5.mean(0) @ w6)
+    b6[-1] += blank_bias
+    w["w6"], w["b6"] = w6, b6.astype(np.float32)
+    return w
+
+
 def model_bytes(weights, labels=ENGLISH_LABELS, sample_rate=16000, win_len=512, win_step=320, n_input=26, n_context=9,
                 n_steps=16, beam_width=500, relu_clip=20.0):
     H = weights["b1"].shape[0]
@@ -65,19 +145,38 @@ def write_model(path, weights, **kw):
         f.write(model_bytes(weights, **kw))
 
 
+_PHONES = None
+
+
+def _phone_inventory(sample_rate):
+    """40 fixed "phones": three sinusoid formants each (frequencies / amplitudes drawn once, seed 4242)."""
+    global _PHONES
+    if _PHONES is None:
+        rng = np.random.default_rng(4242)
+        _PHONES = [(rng.uniform(200, 3800, size=3), rng.uniform(0.3, 1.0, size=3)) for _ in range(40)]
+    return _PHONES
+
+
 def make_pcm(n_samples, utt=0, sample_rate=16000, base_seed=20260922):
-    """Band-limited noise + 3-5 random sinusoid "formants" amplitude-modulated at 4 Hz, int16, peak 0.3 FS."""
+    """Speech-like synthetic audio: a random sequence of "phones" (50-150 ms each, three sinusoid formants from a
+    fixed 40-phone inventory, raised-cosine edges) with ~20 % low-noise pauses, plus a noise floor; int16, peak
+    0.3 FS.  Every utterance shares the same long-term statistics, only the phone sequence differs."""
     rng = np.random.default_rng(base_seed + utt)
     if n_samples <= 0:
         return np.zeros(0, np.int16)
-    t = np.arange(n_samples) / sample_rate
-    x = rng.standard_normal(n_samples)
-    # crude band-limit: moving average of 4 samples
-    x = np.convolve(x, np.ones(4) / 4.0, mode="same") * 0.2
-    for _ in range(rng.integers(3, 6)):
-        f = rng.uniform(200, 3500)
-        x += rng.uniform(0.3, 1.0) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28)) * \
-            (0.5 + 0.5 * np.sin(2 * np.pi * 4 * t + rng.uniform(0, 6.28)))
+    phones = _phone_inventory(sample_rate)
+    x = rng.standard_normal(n_samples) * 0.01
+    pos = 0
+    while pos < n_samples:
+        dur = int(rng.uniform(0.05, 0.15) * sample_rate)
+        seg = min(dur, n_samples - pos)
+        if rng.random() >= 0.2:
+            f, a = phones[int(rng.integers(len(phones)))]
+            t = np.arange(seg) / sample_rate
+            env = 0.5 - 0.5 * np.cos(2 * np.pi * np.minimum(np.arange(seg), seg - 1 - np.arange(seg)).clip(0, 160) / 320.0)
+            sig = sum(ai * np.sin(2 * np.pi * fi * t + rng.uniform(0, 6.28)) for fi, ai in zip(f, a))
+            x[pos:pos + seg] += sig * env
+        pos += seg
     x = x / (np.abs(x).max() + 1e-9) * 0.3 * 32767
     return x.astype(np.int16)
 
