@@ -20,29 +20,29 @@ extern "C" {
 
 #define STT_EXPORT __attribute__((visibility("default")))
 
-typedef struct ModelState ModelState;         /* coqui-stt.h:20 */
-typedef struct StreamingState StreamingState; /* coqui-stt.h:22 */
+typedef struct ModelState ModelState;         /* coqui-stt.h:22 */
+typedef struct StreamingState StreamingState; /* coqui-stt.h:24 */
 
-typedef struct TokenMetadata { /* coqui-stt.h:27-36 */
+typedef struct TokenMetadata { /* coqui-stt.h:29-38 */
   const char* const text;
   const unsigned int timestep;
   const float start_time;
 } TokenMetadata;
 
-typedef struct CandidateTranscript { /* coqui-stt.h:42-52 */
+typedef struct CandidateTranscript { /* coqui-stt.h:44-55 */
   const TokenMetadata* const tokens;
   const unsigned int num_tokens;
   const double confidence;
 } CandidateTranscript;
 
-typedef struct AcousticModelEmissions { /* coqui-stt.h:57-69 */
+typedef struct AcousticModelEmissions { /* coqui-stt.h:65-74 */
   int num_symbols;
   const char** symbols;
   int num_timesteps;
   const double* emissions;
 } AcousticModelEmissions;
 
-typedef struct Metadata { /* coqui-stt.h:74-86 */
+typedef struct Metadata { /* coqui-stt.h:79-86 */
   const CandidateTranscript* const transcripts;
   const unsigned int num_transcripts;
   const AcousticModelEmissions* const emissions;
@@ -81,65 +81,65 @@ enum STT_Error_Codes {
 };
 
 /* ------------------------------------------------------------------------------------------------ PART 1 */
-/* coqui-stt.h:136-138 | stt.cc:374-379 (+ CreateModelImpl :336-372).  Accepts a `.sttw` model file. */
+/* coqui-stt.h:137-138 | stt.cc:374-379 (+ CreateModelImpl :336-372).  Accepts a `.sttw` model file. */
 STT_EXPORT int STT_CreateModel(const char* aModelPath, ModelState** retval);
-/* coqui-stt.h:150-153 | stt.cc:381-387.  The buffer is parsed and copied; it need not outlive the call. */
+/* coqui-stt.h:150-152 | stt.cc:381-387.  The buffer is parsed and copied; it need not outlive the call. */
 STT_EXPORT int STT_CreateModelFromBuffer(const char* aModelBuffer, unsigned int aBufferSize, ModelState** retval);
-/* coqui-stt.h:163 | stt.cc:389-393 */
+/* coqui-stt.h:164 | stt.cc:389-393 */
 STT_EXPORT unsigned int STT_GetModelBeamWidth(const ModelState* aCtx);
 /* coqui-stt.h:176-177 | stt.cc:395-400 */
 STT_EXPORT int STT_SetModelBeamWidth(ModelState* aCtx, unsigned int aBeamWidth);
-/* coqui-stt.h:186 | stt.cc:402-406 */
+/* coqui-stt.h:187 | stt.cc:402-406 */
 STT_EXPORT int STT_GetModelSampleRate(const ModelState* aCtx);
-/* coqui-stt.h:192 | stt.cc:408-412 */
+/* coqui-stt.h:193 | stt.cc:408-412 */
 STT_EXPORT void STT_FreeModel(ModelState* ctx);
-/* coqui-stt.h:203-204 | stt.cc:435-440 (EnableExternalScorerImpl :414-433: any failure -> STT_ERR_INVALID_SCORER) */
+/* coqui-stt.h:204-205 | stt.cc:435-440 (EnableExternalScorerImpl :414-433: any failure -> STT_ERR_INVALID_SCORER) */
 STT_EXPORT int STT_EnableExternalScorer(ModelState* aCtx, const char* aScorerPath);
 /* coqui-stt.h:217-219 | stt.cc:442-449 */
 STT_EXPORT int STT_EnableExternalScorerFromBuffer(ModelState* aCtx, const char* aScorerBuffer, unsigned int aBufferSize);
-/* coqui-stt.h:233-235 | stt.cc:451-467 */
+/* coqui-stt.h:233-235 | stt.cc:451-466 */
 STT_EXPORT int STT_AddHotWord(ModelState* aCtx, const char* word, float boost);
-/* coqui-stt.h:246-247 | stt.cc:469-484 */
+/* coqui-stt.h:246-247 | stt.cc:468-482 */
 STT_EXPORT int STT_EraseHotWord(ModelState* aCtx, const char* word);
-/* coqui-stt.h:257 | stt.cc:486-499 */
+/* coqui-stt.h:257 | stt.cc:484-496 */
 STT_EXPORT int STT_ClearHotWords(ModelState* aCtx);
-/* coqui-stt.h:267 | stt.cc:501-509 */
+/* coqui-stt.h:267 | stt.cc:498-506 */
 STT_EXPORT int STT_DisableExternalScorer(ModelState* aCtx);
-/* coqui-stt.h:279-281 | stt.cc:511-517 */
+/* coqui-stt.h:279-281 | stt.cc:508-517 */
 STT_EXPORT int STT_SetScorerAlphaBeta(ModelState* aCtx, float aAlpha, float aBeta);
 /* coqui-stt.h:295-297 | stt.cc:655-662 */
 STT_EXPORT char* STT_SpeechToText(ModelState* aCtx, const short* aBuffer, unsigned int aBufferSize);
-/* coqui-stt.h:314-317 | stt.cc:664-672 */
+/* coqui-stt.h:315-318 | stt.cc:664-672 */
 STT_EXPORT Metadata* STT_SpeechToTextWithMetadata(ModelState* aCtx, const short* aBuffer, unsigned int aBufferSize,
                                                    unsigned int aNumResults);
 /* coqui-stt.h:334-337 | stt.cc:674-688 */
 STT_EXPORT Metadata* STT_SpeechToTextWithEmissions(ModelState* aCtx, const short* aBuffer, unsigned int aBufferSize,
                                                     unsigned int aNumResults);
-/* coqui-stt.h:350-351 | stt.cc:519-551 */
+/* coqui-stt.h:349-350 | stt.cc:519-551 */
 STT_EXPORT int STT_CreateStream(ModelState* aCtx, StreamingState** retval);
-/* coqui-stt.h:362-364 | stt.cc:587-593 */
+/* coqui-stt.h:361-363 | stt.cc:588-594 */
 STT_EXPORT void STT_FeedAudioContent(StreamingState* aSctx, const short* aBuffer, unsigned int aBufferSize);
-/* coqui-stt.h:375 | stt.cc:595-599 */
+/* coqui-stt.h:374 | stt.cc:596-600 */
 STT_EXPORT char* STT_IntermediateDecode(const StreamingState* aSctx);
-/* coqui-stt.h:389-390 | stt.cc:601-606 */
+/* coqui-stt.h:389-390 | stt.cc:602-607 */
 STT_EXPORT Metadata* STT_IntermediateDecodeWithMetadata(const StreamingState* aSctx, unsigned int aNumResults);
-/* coqui-stt.h:408 | stt.cc:608-613 (does NOT free the stream) */
+/* coqui-stt.h:408 | stt.cc:609-614 (does NOT free the stream) */
 STT_EXPORT char* STT_IntermediateDecodeFlushBuffers(StreamingState* aSctx);
-/* coqui-stt.h:428-429 | stt.cc:615-622 */
+/* coqui-stt.h:428-429 | stt.cc:616-622 */
 STT_EXPORT Metadata* STT_IntermediateDecodeWithMetadataFlushBuffers(StreamingState* aSctx, unsigned int aNumResults);
-/* coqui-stt.h:442 | stt.cc:624-630 */
+/* coqui-stt.h:443 | stt.cc:624-630 */
 STT_EXPORT char* STT_FinishStream(StreamingState* aSctx);
-/* coqui-stt.h:460-461 | stt.cc:632-639 */
+/* coqui-stt.h:461-462 | stt.cc:632-639 */
 STT_EXPORT Metadata* STT_FinishStreamWithMetadata(StreamingState* aSctx, unsigned int aNumResults);
-/* coqui-stt.h:472 | stt.cc:690-694 */
+/* coqui-stt.h:474 | stt.cc:690-694 */
 STT_EXPORT void STT_FreeStream(StreamingState* aSctx);
-/* coqui-stt.h:478 | stt.cc:696-724 */
+/* coqui-stt.h:480 | stt.cc:696-726 */
 STT_EXPORT void STT_FreeMetadata(Metadata* m);
-/* coqui-stt.h:484 | stt.cc:725-729 */
+/* coqui-stt.h:486 | stt.cc:727-731 */
 STT_EXPORT void STT_FreeString(char* str);
-/* coqui-stt.h:492 | stt.cc:731-735 */
+/* coqui-stt.h:495 | stt.cc:733-737 */
 STT_EXPORT char* STT_Version(void);
-/* coqui-stt.h:502 | native_client/stt_errors.cc:5-19 */
+/* coqui-stt.h:504 | native_client/stt_errors.cc:5-19 */
 STT_EXPORT char* STT_ErrorCodeToErrorMessage(int aErrorCode);
 
 /* ------------------------------------------------------------------------------------------------ PART 2 */
