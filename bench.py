@@ -270,7 +270,8 @@ def main():
     roof_all["decode"] = {"bound": "hbm", "achieved": dec_bytes / (stages["decode"] * 1e-3) / 1e9, "peak": hbm_gbs,
                           "unit": "GB/s", "frac": dec_bytes / (stages["decode"] * 1e-3) / 1e9 / hbm_gbs,
                           "ms": stages["decode"], "note": "T-serial scan + gather: latency bound (SURVEY 8d)",
-                          "lm_words_per_utt": Q, "lm_calls_per_utt": lm["lm_calls"] / float(B)}
+                          "lm_words_per_utt": Q, "lm_calls_per_utt": lm["lm_calls"] / float(B),
+                          "phase_share": (lambda pc: {k: round(v / float(max(1, sum(pc.values()))), 3) for k, v in pc.items()})(batch.phase_cycles())}
     dominant = max(roof_all, key=lambda k: roof_all[k]["ms"])
     roofline = dict(roof_all[dominant])
     roofline.update({"kernel": {"dense123": "gemm_tc_kernel<256,clip-relu> x3", "lstm_in": "gemm_tc_kernel<256,bias-f32>",

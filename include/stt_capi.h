@@ -169,6 +169,9 @@ STT_EXPORT int STTX_BatchFetch(STTX_Batch* b);                         /* device
 STT_EXPORT int STTX_BatchGetTimings(STTX_Batch* b, STTX_Timings* out);
 STT_EXPORT long long STTX_BatchKernelLaunches(STTX_Batch* b);
 /* instrumentation: words scored by the LM / LM calls in the last STTX_BatchDecode (decoder roofline's Q) */
+/* instrumentation: SM cycles per decoder phase (gate, child discovery, LM, live update, children, select, commit, -),
+ * summed over the batch's utterances, for the last STTX_BatchDecode */
+STT_EXPORT int STTX_BatchPhaseCycles(STTX_Batch* b, unsigned long long* out8);
 STT_EXPORT int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls);
 /* test hooks */
 STT_EXPORT int STTX_BatchTimesteps(STTX_Batch* b, unsigned int u);

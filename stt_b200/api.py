@@ -55,7 +55,7 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles",
 ]
 
 
@@ -125,6 +125,7 @@ def lib():
     L.STTX_BatchKernelLaunches.argtypes = [vp]
     L.STTX_BatchKernelLaunches.restype = c_longlong
     L.STTX_BatchTimesteps.argtypes = [vp, c_uint]
+    L.STTX_BatchPhaseCycles.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchLmStats.argtypes = [vp, POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchCopyFeatures.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchCopyProbs.argtypes = [vp, c_uint, c_void_p]
@@ -399,6 +400,12 @@ class Batch(object):
         t = _Timings()
         lib().STTX_BatchGetTimings(self._impl, byref(t))
         return {n: getattr(t, n) for n, _ in _Timings._fields_}
+
+    def phase_cycles(self):
+        arr = (ctypes.c_ulonglong * 8)()
+        lib().STTX_BatchPhaseCycles(self._impl, arr)
+        names = ("gate_cutoff", "child_discovery", "lm", "live_update", "children", "select", "commit", "unused")
+        return dict(zip(names, [int(x) for x in arr]))
 
     def lm_stats(self):
         w, c = ctypes.c_ulonglong(), ctypes.c_ulonglong()

@@ -553,6 +553,9 @@ int STTX_BatchGetTimings(STTX_Batch* b, STTX_Timings* out) {
   return STT_ERR_OK;
 }
 long long STTX_BatchKernelLaunches(STTX_Batch* b) { return stteng::batch_kernel_launches(b->dev); }
+int STTX_BatchPhaseCycles(STTX_Batch* b, unsigned long long* out8) {
+  return stteng::batch_phase_cycles(b->dev, out8) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
+}
 int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls) {
   return stteng::batch_lm_stats(b->dev, words_scored, lm_calls) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
 }

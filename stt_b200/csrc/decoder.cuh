@@ -6,6 +6,8 @@
 // arithmetic types of SURVEY.md appendix A (f32 log-probs through glibc-exact logf/expf, f64 only where the
 // reference uses it).  The data structure is NOT a port:
 //
+//   (v2: live lists and per-step candidates live in SHARED memory, the dictionary FST is pre-digested into per-state
+//   label masks + pre-resolved next states, arena nodes are 32-byte records, LM results are cached per node.)
 //   * The reference keeps a pointer trie and walks it depth-first every step.  Semantically each step maps a SET of
 //     <= beam live prefixes to the top-beam of (live prefixes U their one-character extensions); a pruned node that
 //     is later re-created gets exactly the values a fresh node gets (path_trie.cpp:45-52).  So we keep a flat
@@ -38,40 +40,54 @@ constexpr float kNegMax = -3.402823466e+38f;  // -NUM_FLT_INF (decoder_utils.h:1
 constexpr float kFltMin = 1.175494351e-38f;   // NUM_FLT_MIN
 constexpr int kMaxClasses = 64;
 constexpr int kMaxWordBytes = 128;
+constexpr int kStateWords = sttscorer::kMaxOrder - 1;
+
+struct Node {            // one surviving prefix (PathTrie node), 32 bytes
+  uint32_t parent;       // arena id, kNone for the root
+  uint32_t chr;          // label, kRootChar for the root
+  int32_t dict;          // dictionary-FST state AFTER this label (already reset to Start() after a final state)
+  uint32_t last_space;   // nearest ancestor-or-self whose label is the space, or kNone
+  uint32_t word_id;      // for space nodes: vocabulary id of the word they terminate
+  uint32_t live_slot;    // index in the current live list, or kNone
+  uint32_t lm_wid;       // LM cache valid flag / word id of the word ending here (kNone = not computed)
+  uint32_t pad;
+};
+struct HtSlot {          // (parent node, label) -> node id, open addressing; key 0 = empty
+  unsigned long long key;
+  uint32_t val, pad;
+};
 
 // Per-utterance device state ("stream slot").  All pointers are device memory sized for (beam_cap, t_cap).
 struct Slot {
-  // arena of surviving prefix nodes; node 0 is the root
-  uint32_t* parent;      // [arena_cap]
-  uint32_t* chr;         // [arena_cap]  label, kRootChar for the root
-  int32_t* dict_state;   // [arena_cap]
-  uint32_t* last_space;  // [arena_cap]  nearest ancestor-or-self whose label is the space, or kNone
-  uint32_t* word_id;     // [arena_cap]  for space nodes: vocab id of the word they terminate
-  uint32_t* live_slot;   // [arena_cap]  index in the current live list, or kNone
-  // (parent node, label) -> node id for every node ever created: a pruned node that still has live descendants must
-  // be REVIVED under its old id when its prefix re-enters the beam (path_trie.cpp:45-52), so that those
-  // descendants keep merging into it.
-  unsigned long long* ht_key;  // [ht_mask + 1], 0 = empty, zero-initialised by the host
-  uint32_t* ht_val;
+  Node* nodes;           // [arena_cap]; node 0 is the root
+  // A pruned node that still has live descendants must be REVIVED under its old id when its prefix re-enters the beam
+  // (path_trie.cpp:45-52), so that those descendants keep merging into it: every node ever created is findable here.
+  HtSlot* ht;            // [ht_mask + 1], zero-initialised by the host
   uint32_t ht_mask;
+  // Per-node LM cache, keyed by the node that ENDS a word: the natural-log conditional probability of that word given
+  // its history (Scorer::get_log_cond_prob's return value), its vocabulary id, and the KenLM state after it.  The
+  // reference recomputes the whole <=order-word window on every call (scorer.cpp:307-344, 369-396); scoring the last
+  // word from the carried state is value-identical (the KenLM state after k words is exactly the context the next
+  // lookup may use; from-BOS carry == the window's BeginSentence chain when the window holds the whole history, and
+  // the <=order-1 words a state can hold all lie inside the window otherwise), and a node's word/history never change.
+  double* lm_cond;       // [arena_cap]
+  uint32_t* lm_sw;       // [arena_cap * kStateWords] state words
+  float* lm_sb;          // [arena_cap * kStateWords] state backoffs
+  uint32_t* lm_meta;     // [arena_cap]  state length | oov distance << 8 | words in history (saturating) << 16
   // timestep tree (path_trie.h:17-37): ts node 0 is the root
   uint32_t* ts_parent;   // [ts_cap]
   uint32_t* ts_val;      // [ts_cap]
-  // live lists, double buffered (cur = live_sel)
-  float* score[2];
-  float* b_prev[2];
-  float* nb_prev[2];
-  uint32_t* node[2];
-  uint32_t* ts[2];
-  // per-step candidates, capacity cand_cap = beam_cap * n_classes
-  float* c_score;
-  uint32_t *c_a, *c_b, *c_c, *c_d;
-  uint64_t* c_key;
-  // per-live scratch
-  float* lm_term;        // [beam_cap] (float)((cond_prob + boost) * alpha) for "prefix i + space"
-  uint32_t* lm_word;     // [beam_cap] vocab id of the word completed by that space
-  // scalars (persist across launches for streaming)
-  uint32_t* scalars;     // [16]: 7 LM words scored, 8 LM calls; 0 n_live, 1 live_sel, 2 arena_count, 3 ts_count, 4 abs_time_step, 5 start_expanding, 6 overflow
+  // live list as left by the last launch (the step kernel works on a shared-memory copy)
+  float *score, *b_prev, *nb_prev;   // [beam_cap]
+  uint32_t *node, *ts;               // [beam_cap]
+  // per-step candidates when they do not fit in shared memory, and scratch for finalize; capacity cand_cap
+  unsigned long long* c_key;
+  uint32_t *c_p0, *c_p1;
+  unsigned long long* phase_cycles;  // [8] instrumentation: SM cycles per phase (thread 0's clock)
+  // scalars: 0 n_live, 2 arena_count, 3 ts_count, 4 abs_time_step, 5 start_expanding, 6 overflow,
+  //          7 LM words scored (reference-equivalent window sizes), 8 LM calls, 9 max candidates in a step,
+  //          10 steps that spilled candidates to global memory
+  uint32_t* scalars;     // [16]
   uint32_t arena_cap, ts_cap, beam_cap, cand_cap;
 };
 
@@ -81,6 +97,10 @@ struct DecodeParams {
   int space_id;
   int has_scorer;
   sttscorer::ScorerView scorer;
+  // dictionary FST, pre-digested on the host (engine.cu build_fst_tables): per state {first arc, bit mask of the labels
+  // that have an arc}, per arc {ilabel, dictionary state of the child = Start() if the arc's target is final}
+  const uint2* fst_state2;
+  const int2* fst_arc2;
 };
 
 struct StepInput {
@@ -101,18 +121,21 @@ __device__ __forceinline__ unsigned long long ht_make_key(uint32_t parent_node, 
 __device__ __forceinline__ uint32_t ht_find(const Slot& s, unsigned long long key) {
   uint32_t h = ht_hash(key) & s.ht_mask;
   for (;;) {
-    const unsigned long long k = s.ht_key[h];
-    if (k == key) return s.ht_val[h];
-    if (k == 0ull) return 0xffffffffu;
+    const ulonglong2 slot = *reinterpret_cast<const ulonglong2*>(&s.ht[h]);
+    if (slot.x == key) return (uint32_t)slot.y;
+    if (slot.x == 0ull) return kNone;
     h = (h + 1) & s.ht_mask;
   }
 }
 __device__ __forceinline__ void ht_insert(const Slot& s, unsigned long long key, uint32_t val) {
   uint32_t h = ht_hash(key) & s.ht_mask;
   for (;;) {
-    const unsigned long long prev = atomicCAS(&s.ht_key[h], 0ull, key);
-    if (prev == 0ull || prev == key) {
-      s.ht_val[h] = val;
+    // the value is written before the key is published; distinct threads insert distinct keys
+    const unsigned long long prev = atomicCAS(&s.ht[h].key, 0ull, 0xffffffffffffffffull);
+    if (prev == 0ull) {
+      s.ht[h].val = val;
+      __threadfence_block();
+      atomicExch(&s.ht[h].key, key);
       return;
     }
     h = (h + 1) & s.ht_mask;
@@ -122,6 +145,14 @@ __device__ __forceinline__ uint32_t sortable(float f) {
   uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ float unsortable(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ unsigned long long make_key(float score, uint32_t chr, uint32_t idx) {
+  // descending order == the reference's prefix_compare (score desc, then character asc), then candidate index asc
+  return ((unsigned long long)sortable(score) << 32) | ((unsigned long long)(255u - (chr & 0xffu)) << 24) |
+         (unsigned long long)(0xffffffu - (idx & 0xffffffu));
+}
 // order in which the reference's sorted loop visits two live prefixes: true if x comes before y
 __device__ __forceinline__ bool visits_before(float sx, uint32_t cx, uint32_t ix, float sy, uint32_t cy, uint32_t iy) {
   if (sx != sy) return sx > sy;
@@ -129,22 +160,19 @@ __device__ __forceinline__ bool visits_before(float sx, uint32_t cx, uint32_t ix
   return ix < iy;
 }
 
-// Scorer::make_ngram + get_log_cond_prob for "prefix `node` followed by a space" (word mode).
-// Returns (float)(cond_prob * alpha) exactly as ctc_beam_search_decoder.cpp:239 computes it (hot-word boost = 0)
-// and the vocabulary id of the completed word.
-__device__ float lm_space_term(const Slot& s, const sttscorer::ScorerView& v, uint32_t node, uint32_t* word_out,
-                               uint32_t* n_words_out = nullptr) {
+// Scorer::make_ngram + get_log_cond_prob, literally as the reference does it (walk back <= order words, score the
+// window from BeginSentence / NullContext).  Fallback when a history node has no cached state.
+__device__ double lm_window_cond(const Slot& s, const sttscorer::ScorerView& v, uint32_t node, uint32_t* word_out,
+                                 uint32_t* n_words_out) {
   uint32_t ids_rev[sttscorer::kMaxOrder];
   int n = 0;
   uint32_t first_word = 0;
   const int order = (int)v.order;
-  // Scorer::make_ngram (scorer.cpp:369-396): walk back word by word.  `term` is the space node that terminated
-  // the word ending at `cur` (kNone for the first, possibly unfinished, word); its vocab id is cached on it.
   uint32_t cur = node, term = kNone;
   while (n < order) {
-    const uint32_t cc = s.chr[cur];
+    const uint32_t cc = s.nodes[cur].chr;
     if (cc == kRootChar) break;
-    const uint32_t stop = s.last_space[cur];  // == cur when cur is itself a space (empty word)
+    const uint32_t stop = s.nodes[cur].last_space;  // == cur when cur is itself a space (empty word)
     uint32_t id;
     if (cc == (uint32_t)v.space_label) {
       id = 0;  // get_prev_word returns an empty word: never in the vocabulary
@@ -152,8 +180,8 @@ __device__ float lm_space_term(const Slot& s, const sttscorer::ScorerView& v, ui
       uint8_t buf[kMaxWordBytes];
       int len = 0;
       bool too_long = false;
-      for (uint32_t w = cur; w != stop && s.chr[w] != kRootChar; w = s.parent[w]) {
-        const uint32_t c = s.chr[w];
+      for (uint32_t w = cur; w != stop && s.nodes[w].chr != kRootChar; w = s.nodes[w].parent) {
+        const uint32_t c = s.nodes[w].chr;
         const int l = v.label_len[c];
         if (len + l > kMaxWordBytes) { too_long = true; break; }
         for (int q = l - 1; q >= 0; --q) buf[len++] = v.label_bytes[c][q];
@@ -162,27 +190,115 @@ __device__ float lm_space_term(const Slot& s, const sttscorer::ScorerView& v, ui
       id = too_long ? 0u : sttscorer::vocab_index(v, buf, (uint32_t)len);
       first_word = id;
     } else {
-      id = s.word_id[term];
+      id = s.nodes[term].word_id;
     }
     ids_rev[n++] = id;
     if (stop == kNone) break;
     term = stop;
-    cur = s.parent[stop];
+    cur = s.nodes[stop].parent;
   }
   *word_out = first_word;
-  if (n_words_out) *n_words_out = (uint32_t)n;
+  *n_words_out = (uint32_t)n;
   uint32_t ids[sttscorer::kMaxOrder];
   for (int i = 0; i < n; ++i) ids[i] = ids_rev[n - 1 - i];
-  const bool bos = n < order;
-  const double cond = sttscorer::log_cond_prob_ids(v, ids, n, bos);
-  return (float)(cond * v.alpha);
+  return sttscorer::log_cond_prob_ids(v, ids, n, n < order);
 }
 
-// Same, for DecoderState::decode's rescoring of an unfinished last word (:288-300): make_ngram(prefix) where the
-// last "word" is the partial word ending at `node`.
-__device__ float lm_final_term(const Slot& s, const sttscorer::ScorerView& v, uint32_t node) {
-  uint32_t dummy;
-  return lm_space_term(s, v, node, &dummy);
+// Cached evaluation of get_log_cond_prob(make_ngram(prefix `node`), bos) -- see Slot::lm_cond.
+__device__ double lm_eval_node(const Slot& s, const sttscorer::ScorerView& v, uint32_t node, uint32_t* word_out,
+                               uint32_t* n_window_out) {
+  const int order = (int)v.order;
+  const Node nd = s.nodes[node];
+  if (nd.lm_wid != kNone) {
+    *word_out = nd.lm_wid;
+    const uint32_t nw = s.lm_meta[node] >> 16;
+    *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
+    return s.lm_cond[node];
+  }
+  const uint32_t cc = nd.chr;
+  double cond;
+  uint32_t wid = 0, meta;
+  sttscorer::LmState out;
+  out.length = 0;
+  if (cc == kRootChar) {
+    // empty prefix: make_ngram returns no words, get_log_cond_prob of nothing is 0 (scorer.cpp:325,343)
+    cond = 0.0;
+    sttscorer::begin_sentence_state(v, out);
+    meta = (uint32_t)out.length | (255u << 8) | (0u << 16);
+  } else {
+    // ---- the word ending at `node`
+    const uint32_t stop = nd.last_space;  // == node when node is itself a space (empty word)
+    if (cc != (uint32_t)v.space_label) {
+      uint8_t buf[kMaxWordBytes];
+      int len = 0;
+      bool too_long = false;
+      uint32_t w = node;
+      Node wn = nd;
+      while (w != stop && wn.chr != kRootChar) {
+        const int l = v.label_len[wn.chr];
+        if (len + l > kMaxWordBytes) { too_long = true; break; }
+        for (int q = l - 1; q >= 0; --q) buf[len++] = v.label_bytes[wn.chr][q];
+        w = wn.parent;
+        if (w == kNone) break;
+        wn = s.nodes[w];
+      }
+      for (int a = 0, b = len - 1; a < b; ++a, --b) { const uint8_t t = buf[a]; buf[a] = buf[b]; buf[b] = t; }
+      wid = too_long ? 0u : sttscorer::vocab_index(v, buf, (uint32_t)len);
+    }
+    // ---- history state: the word-final node before the space that precedes this word
+    sttscorer::LmState ctx;
+    uint32_t ctx_oov = 255, ctx_words = 0;
+    bool have_ctx = true;
+    if (stop == kNone) {
+      sttscorer::begin_sentence_state(v, ctx);
+    } else {
+      const uint32_t prev_end = s.nodes[stop].parent;
+      const Node pe = s.nodes[prev_end];
+      if (pe.chr == kRootChar || pe.chr == (uint32_t)v.space_label) {
+        // the previous "word" is empty (leading / double space): it is an OOV inside the window
+        sttscorer::null_context_state(ctx);
+        ctx_oov = 0;
+        ctx_words = 1;
+      } else if (pe.lm_wid != kNone) {
+        const uint32_t m = s.lm_meta[prev_end];
+        ctx.length = (uint8_t)(m & 0xffu);
+        ctx_oov = (m >> 8) & 0xffu;
+        ctx_words = m >> 16;
+        for (int i = 0; i < (int)ctx.length; ++i) {
+          ctx.words[i] = s.lm_sw[(size_t)prev_end * kStateWords + i];
+          ctx.backoff[i] = s.lm_sb[(size_t)prev_end * kStateWords + i];
+        }
+      } else {
+        have_ctx = false;
+      }
+    }
+    if (!have_ctx) return lm_window_cond(s, v, node, word_out, n_window_out);  // not cached: no state to carry
+    uint32_t oov_dist;
+    if (wid == 0) {
+      sttscorer::null_context_state(out);
+      oov_dist = 0;
+      cond = -1000.0;  // OOV_SCORE, returned undivided (scorer.cpp:328-331)
+    } else {
+      const float p10 = sttscorer::full_score(v, ctx, wid, out);
+      oov_dist = ctx_oov >= 254 ? 255u : ctx_oov + 1;
+      // an OOV word among the previous order-1 words is still inside the reference's window
+      cond = (oov_dist <= (uint32_t)(order - 1)) ? -1000.0 : (double)p10 / (double)0.4342944819f;
+    }
+    const uint32_t nwords = ctx_words >= 0xfffeu ? 0xffffu : ctx_words + 1;
+    meta = (uint32_t)out.length | (oov_dist << 8) | (nwords << 16);
+  }
+  for (int i = 0; i < (int)out.length; ++i) {
+    s.lm_sw[(size_t)node * kStateWords + i] = out.words[i];
+    s.lm_sb[(size_t)node * kStateWords + i] = out.backoff[i];
+  }
+  s.lm_meta[node] = meta;
+  s.lm_cond[node] = cond;
+  __threadfence_block();
+  s.nodes[node].lm_wid = wid;
+  *word_out = wid;
+  const uint32_t nw = meta >> 16;
+  *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
+  return cond;
 }
 
 // ------------------------------------------------------------------------------------------------ init
@@ -191,58 +307,77 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start)
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= n_slots) return;
   Slot& s = slots[u];
-  s.parent[0] = kNone;
-  s.chr[0] = kRootChar;
-  s.dict_state[0] = fst_start;
-  s.last_space[0] = kNone;
-  s.word_id[0] = 0;
-  s.live_slot[0] = 0;
+  Node root;
+  root.parent = kNone; root.chr = kRootChar; root.dict = fst_start; root.last_space = kNone; root.word_id = 0;
+  root.live_slot = 0; root.lm_wid = kNone; root.pad = 0;
+  s.nodes[0] = root;
   s.ts_parent[0] = kNone;
   s.ts_val[0] = 0;
-  s.score[0][0] = 0.f;
-  s.b_prev[0][0] = 0.f;
-  s.nb_prev[0][0] = kNegMax;
-  s.node[0][0] = 0;
-  s.ts[0][0] = 0;
+  s.score[0] = 0.f;
+  s.b_prev[0] = 0.f;
+  s.nb_prev[0] = kNegMax;
+  s.node[0] = 0;
+  s.ts[0] = 0;
+  for (int q = 0; q < 16; ++q) s.scalars[q] = 0;
   s.scalars[0] = 1;  // n_live
-  s.scalars[1] = 0;  // live_sel
   s.scalars[2] = 1;  // arena_count
   s.scalars[3] = 1;  // ts_count
-  s.scalars[4] = 0;  // abs_time_step
-  s.scalars[5] = 0;  // start_expanding
-  s.scalars[6] = 0;  // overflow flag
-  s.scalars[7] = 0;
-  s.scalars[8] = 0;
+  for (int q = 0; q < 8; ++q) s.phase_cycles[q] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ step kernel
-// Block-wide exclusive scan of one 0/1 flag per thread; returns the thread's offset and the block total.
+// Block-wide exclusive scan of one count per thread; returns the thread's offset and the block total.
 template <int NT>
-__device__ __forceinline__ uint32_t block_scan_flag(bool flag, uint32_t* warp_sums /*[NT/32 + 1]*/, uint32_t& total) {
-  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+__device__ __forceinline__ uint32_t block_scan(uint32_t cnt, uint32_t* warp_sums /*[NT/32 + 1]*/, uint32_t& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t in_warp = __popc(ballot & ((1u << lane) - 1));
-  if (lane == 0) warp_sums[warp] = __popc(ballot);
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    uint32_t v = (lane < NT / 32) ? warp_sums[lane] : 0;
-    uint32_t incl = v;
+    uint32_t v = (lane < NT / 32) ? warp_sums[lane] : 0, inc2 = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc2, d);
+      if (lane >= d) inc2 += o;
     }
-    if (lane < NT / 32) warp_sums[lane] = incl - v;
-    if (lane == 31) warp_sums[NT / 32] = incl;
+    if (lane < NT / 32) warp_sums[lane] = inc2 - v;
+    if (lane == 31) warp_sums[NT / 32] = inc2;
   }
   __syncthreads();
-  const uint32_t off = warp_sums[warp] + in_warp;
+  const uint32_t off = warp_sums[warp] + (incl - cnt);
   total = warp_sums[NT / 32];
   __syncthreads();
   return off;
 }
 
-template <int NT>
+// Shared-memory image of one live list.
+template <int WC>
+struct LiveList {
+  float score[WC], b[WC], nb[WC];
+  uint32_t node[WC], ts[WC], pnode[WC], lsp[WC], pos[WC], mask[WC];
+  int32_t dict[WC];
+  uint8_t chr[WC];
+};
+
+template <int WC, int NC>
+struct StepSmem {
+  LiveList<WC> live[2];
+  uint32_t child[WC];     // phase 2: labels that already have a live child; phase 4+: labels to create
+  uint32_t plive[WC];     // live index of the parent, or kNone
+  uint32_t tsprev[WC];    // timestep-tree parent chosen for an updated live prefix (kNone = keep)
+  uint32_t lmq[WC];       // LM work list
+  uint32_t lmwid[WC];
+  float lmterm[WC];
+  unsigned long long key[NC > 0 ? NC : 1];
+  uint32_t p0[NC > 0 ? NC : 1], p1[NC > 0 ? NC : 1];
+};
+
+template <int NT, int WC, int NC>
 __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
   Slot& s = slots[blockIdx.x];
   const StepInput in = inputs[blockIdx.x];
@@ -251,144 +386,199 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   const int blank = C - 1;
   const int W = p.beam;
   const sttscorer::ScorerView& sv = p.scorer;
+  const uint32_t all_labels = (blank >= 32) ? 0xffffffffu : ((1u << blank) - 1u);
 
   __shared__ float s_logp[kMaxClasses];
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_warp[NT / 32 + 1];
   __shared__ float s_red[NT / 32];
   __shared__ uint32_t s_u[8];
-  __shared__ float s_f[4];
-  extern __shared__ uint32_t s_dyn[];  // [beam_cap] child masks, then [beam_cap] LM work list
-  uint32_t* s_child = s_dyn;
-  uint32_t* s_lmq = s_dyn + s.beam_cap;
+  __shared__ unsigned long long s_ph[8];
+  extern __shared__ __align__(16) uint8_t s_dyn[];
+  StepSmem<WC, NC>& sm = *reinterpret_cast<StepSmem<WC, NC>*>(s_dyn);
 
   uint32_t n_live = s.scalars[0];
-  uint32_t sel = s.scalars[1];
   uint32_t arena_count = s.scalars[2];
   uint32_t ts_count = s.scalars[3];
   uint32_t abs_t = s.scalars[4];
   uint32_t start_expanding = s.scalars[5];
   uint32_t overflow = s.scalars[6];
-  if (threadIdx.x == 0) { s_u[6] = 0; s_u[7] = 0; }
+  uint32_t max_cand = 0, spills = 0;
+  if (tid == 0) {
+    s_u[6] = 0;
+    s_u[7] = 0;
+    for (int q = 0; q < 8; ++q) s_ph[q] = 0;
+  }
+  // ---- load the live list left by the previous launch
+  int cur = 0;
+  for (uint32_t i = tid; i < n_live; i += NT) {
+    LiveList<WC>& L = sm.live[0];
+    const uint32_t nd = s.node[i];
+    const Node n = s.nodes[nd];
+    L.score[i] = s.score[i];
+    L.b[i] = s.b_prev[i];
+    L.nb[i] = s.nb_prev[i];
+    L.node[i] = nd;
+    L.ts[i] = s.ts[i];
+    L.pnode[i] = n.parent;
+    L.lsp[i] = n.last_space;
+    L.dict[i] = n.dict;
+    L.chr[i] = (uint8_t)n.chr;
+    uint2 st = make_uint2(0u, all_labels);
+    if (p.has_scorer) st = p.fst_state2[n.dict];
+    L.pos[i] = st.x;
+    L.mask[i] = st.y;
+  }
+  __syncthreads();
+  long long ph_t0 = clock64();
+#define PHASE_MARK(k) do { if (tid == 0) { const long long _t = clock64(); s_ph[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
 
   for (int step = 0; step < in.n_steps; ++step, ++abs_t) {
     const float* prob = in.probs + (size_t)step * C;
-    // ---- phase 0: gate (:125-132) and class log-probs (get_pruned_emissions :328-358 with the C-API's
-    //      cutoff_prob = 1.0, cutoff_top_n = 40 >= n_classes: no pruning, index order, blank last)
+    LiveList<WC>& L = sm.live[cur];
+    LiveList<WC>& Nx = sm.live[cur ^ 1];
+    // ---- phase 0: gate (:125-132), class log-probs (get_pruned_emissions :328-358 with the C-API's cutoff_prob = 1.0,
+    //      cutoff_top_n = 40 >= n_classes: no pruning, index order, blank last) and the beam's minimum score
     if (tid < C) s_logp[tid] = sttmath::glibc_logf(prob[tid] + kFltMin);
     if (tid == 0) {
       if ((double)prob[blank] < 0.999) start_expanding = 1;
       s_u[0] = start_expanding;
+      s_u[1] = 0;  // LM queue length
     }
-    __syncthreads();
-    start_expanding = s_u[0];
-    if (!start_expanding) { __syncthreads(); continue; }
-    if (overflow) { __syncthreads(); continue; }
-
-    const float* L_score = s.score[sel];
-    const float* L_b = s.b_prev[sel];
-    const float* L_nb = s.nb_prev[sel];
-    const uint32_t* L_node = s.node[sel];
-    const uint32_t* L_ts = s.ts[sel];
-
-    // ---- phase 1: min_cutoff (:134-146)
-    float min_cutoff = kNegMax;
-    bool full_beam = false;
-    if (p.has_scorer) {
+    {
       float m = 3.402823466e+38f;
-      for (uint32_t i = tid; i < n_live; i += NT) m = fminf(m, L_score[i]);
+      for (uint32_t i = tid; i < n_live; i += NT) m = fminf(m, L.score[i]);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
       if ((tid & 31) == 0) s_red[tid >> 5] = m;
-      __syncthreads();
-      if (tid == 0) {
-        float mm = s_red[0];
-        for (int w = 1; w < NT / 32; ++w) mm = fminf(mm, s_red[w]);
-        const double beta_pos = sv.beta > 0.0 ? sv.beta : 0.0;
-        s_f[0] = (float)((double)mm + log((double)prob[blank]) - beta_pos);
-      }
-      __syncthreads();
-      min_cutoff = s_f[0];
+    }
+    for (uint32_t i = tid; i < n_live; i += NT) sm.child[i] = 0;
+    __syncthreads();
+    start_expanding = s_u[0];
+    if (!start_expanding || overflow) { __syncthreads(); continue; }
+    // min_cutoff (:134-146), computed redundantly by every thread to save a barrier
+    float min_cutoff = kNegMax;
+    bool full_beam = false;
+    if (p.has_scorer) {
+      float mm = s_red[0];
+#pragma unroll
+      for (int w = 1; w < NT / 32; ++w) mm = fminf(mm, s_red[w]);
+      const double beta_pos = sv.beta > 0.0 ? sv.beta : 0.0;
+      min_cutoff = (float)((double)mm + log((double)prob[blank]) - beta_pos);
       full_beam = (n_live == (uint32_t)W);
     }
-    for (uint32_t i = tid; i < n_live; i += NT) s_child[i] = 0;
-    if (tid == 0) s_u[1] = 0;  // LM queue length
-    __syncthreads();
+    PHASE_MARK(0);
 
     // ---- phase 2: which (parent, label) pairs already have a live child
     for (uint32_t j = tid; j < n_live; j += NT) {
-      const uint32_t nd = L_node[j];
-      const uint32_t pn = s.parent[nd];
+      const uint32_t pn = L.pnode[j];
+      uint32_t pi = kNone;
       if (pn != kNone) {
-        const uint32_t pi = s.live_slot[pn];
-        if (pi != kNone) atomicOr(&s_child[pi], 1u << s.chr[nd]);
+        pi = s.nodes[pn].live_slot;
+        if (pi != kNone) atomicOr(&sm.child[pi], 1u << L.chr[j]);
       }
+      sm.plive[j] = pi;
     }
     __syncthreads();
+    PHASE_MARK(1);
 
-    // ---- phase 2b: LM work list: live prefixes that will be extended by the space this step
+    // ---- phase 2b: LM terms of the live prefixes that will be extended by the space this step
     if (p.has_scorer) {
       for (uint32_t i = tid; i < n_live; i += NT) {
-        const float sc = L_score[i];
+        const float sc = L.score[i];
         if (sc == kNegMax) continue;
         if (full_beam && s_logp[p.space_id] + sc < min_cutoff) continue;
-        bool need = (s_child[i] >> p.space_id) & 1u;
-        if (!need) need = sttscorer::fst_find(sv, s.dict_state[L_node[i]], p.space_id + 1) >= 0;
-        if (need) s_lmq[atomicAdd(&s_u[1], 1u)] = i;
+        if (((sm.child[i] | L.mask[i]) >> p.space_id) & 1u) sm.lmq[atomicAdd(&s_u[1], 1u)] = i;
       }
       __syncthreads();
       const uint32_t n_lm = s_u[1];
-      // spread items across warps: item q -> thread (q % NW) * 32 + q / NW
       constexpr int NW = NT / 32;
       for (uint32_t base = 0; base < n_lm; base += NT) {
         const int w = tid >> 5, l = tid & 31;
-        const uint32_t q = base + (uint32_t)(l * NW + w);
+        const uint32_t q = base + (uint32_t)(l * NW + w);  // spread the items over the warps
         if (q < n_lm) {
-          const uint32_t i = s_lmq[q];
+          const uint32_t i = sm.lmq[q];
           uint32_t wid, nw;
-          s.lm_term[i] = lm_space_term(s, sv, L_node[i], &wid, &nw);
-          s.lm_word[i] = wid;
-          atomicAdd(&s_u[6], nw);  // instrumentation: words scored (Q of SURVEY 8d's decoder roofline)
-          atomicAdd(&s_u[7], 1u);  // LM calls
+          // (float)(cond * alpha): ctc_beam_search_decoder.cpp:239 (hot-word boost = 0)
+          sm.lmterm[i] = (float)(lm_eval_node(s, sv, L.node[i], &wid, &nw) * sv.alpha);
+          sm.lmwid[i] = wid;
+          atomicAdd(&s_u[6], nw);
+          atomicAdd(&s_u[7], 1u);
         }
       }
       __syncthreads();
     }
+    PHASE_MARK(2);
+
+    // ---- phase 4a: which children each live prefix creates (labels allowed by the dictionary, without a live child,
+    //      above the cutoff); count and scan so that candidates land at deterministic offsets
+    uint32_t n_new = 0;
+    {
+      uint32_t run_base = 0;
+      for (uint32_t base = 0; base < n_live; base += NT) {
+        const uint32_t i = base + tid;
+        uint32_t allow = 0;
+        if (i < n_live) {
+          const float si = L.score[i];
+          if (si != kNegMax) {
+            allow = L.mask[i] & all_labels & ~sm.child[i];
+            if (full_beam) {
+              uint32_t m = allow;
+              while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                if (s_logp[c] + si < min_cutoff) allow &= ~(1u << c);
+              }
+            }
+          }
+        }
+        uint32_t total;
+        const uint32_t off = run_base + block_scan<NT>(__popc(allow), s_warp, total);
+        if (i < n_live) {
+          sm.child[i] = allow;   // the live-child masks are no longer needed (phase 3 uses plive)
+          sm.lmq[i] = off;       // reuse: offset of this prefix's first child among the new candidates
+        }
+        run_base += total;
+      }
+      n_new = run_base;
+    }
+    const uint32_t N = n_live + n_new;
+    if (N > s.cand_cap) { overflow = 1; __syncthreads(); continue; }
+    max_cand = N > max_cand ? N : max_cand;
+    const bool in_smem = (NC > 0) && (N <= (uint32_t)NC);
+    if (!in_smem) ++spills;
+    unsigned long long* const K = in_smem ? sm.key : s.c_key;
+    uint32_t* const P0 = in_smem ? sm.p0 : s.c_p0;
+    uint32_t* const P1 = in_smem ? sm.p1 : s.c_p1;
 
     // ---- phase 3: updated values of the live prefixes (blank / repeat / pulled extension), :150-256
     for (uint32_t j = tid; j < n_live; j += NT) {
-      const float sj = L_score[j];
-      const uint32_t nd = L_node[j];
-      const uint32_t cj = s.chr[nd];
+      const float sj = L.score[j];
+      const uint32_t cj = (L.chr[j] == (uint8_t)kRootChar) ? kRootChar : (uint32_t)L.chr[j];
       float nb = kNegMax, bcur = kNegMax;
       uint32_t ts_prev = kNone;  // kNone = keep current timesteps
-      // extension pulled from a live parent
-      bool has_ext = false;
+      bool has_ext = false, parent_first = false;
       float lp_ext = kNegMax;
       uint32_t ts_par = kNone;
-      bool parent_first = false;
-      const uint32_t pn = s.parent[nd];
-      if (pn != kNone) {
-        const uint32_t pi = s.live_slot[pn];
-        if (pi != kNone) {
-          const float sp = L_score[pi];
-          const float lc = s_logp[cj];
-          if (sp != kNegMax && !(full_beam && lc + sp < min_cutoff)) {
-            has_ext = true;
-            const uint32_t cp = s.chr[pn];
-            if (cj == cp) {
-              const float bp = L_b[pi];
-              lp_ext = (bp > kNegMax) ? lc + bp : kNegMax;
-            } else {
-              lp_ext = lc + sp;
-            }
-            if (p.has_scorer && (int)cj == p.space_id) {
-              lp_ext += s.lm_term[pi];
-              lp_ext = (float)((double)lp_ext + sv.beta);
-            }
-            ts_par = L_ts[pi];
-            parent_first = visits_before(sp, cp, pi, sj, cj, j);
+      const uint32_t pi = sm.plive[j];
+      if (pi != kNone) {
+        const float sp = L.score[pi];
+        const float lc = s_logp[cj];
+        if (sp != kNegMax && !(full_beam && lc + sp < min_cutoff)) {
+          has_ext = true;
+          const uint32_t cp = (L.chr[pi] == (uint8_t)kRootChar) ? kRootChar : (uint32_t)L.chr[pi];
+          if (cj == cp) {
+            const float bp = L.b[pi];
+            lp_ext = (bp > kNegMax) ? lc + bp : kNegMax;
+          } else {
+            lp_ext = lc + sp;
           }
+          if (p.has_scorer && (int)cj == p.space_id) {
+            lp_ext += sm.lmterm[pi];
+            lp_ext = (float)((double)lp_ext + sv.beta);
+          }
+          ts_par = L.ts[pi];
+          parent_first = visits_before(sp, cp, pi, sj, cj, j);
         }
       }
       const bool alive = (sj != kNegMax);
@@ -396,7 +586,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       float lp_rep = kNegMax;
       if (alive && cj != kRootChar && !(full_beam && s_logp[cj] + sj < min_cutoff)) {
         has_rep = true;
-        lp_rep = s_logp[cj] + L_nb[j];
+        lp_rep = s_logp[cj] + L.nb[j];
       }
       if (has_ext && parent_first) {
         if (nb < lp_ext) ts_prev = ts_par;
@@ -416,114 +606,47 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         bcur = lp_b;  // log_sum_exp(-FLT_MAX, lp_b)
       }
       const float ns = sttmath::log_sum_exp(bcur, nb);
-      s.c_score[j] = ns;
-      s.c_a[j] = __float_as_uint(bcur);
-      s.c_b[j] = __float_as_uint(nb);
-      s.c_c[j] = ts_prev;
-      s.c_key[j] = ((uint64_t)sortable(ns) << 32) | ((uint64_t)(255u - cj) << 24) | (uint64_t)(0xffffffu - j);
+      K[j] = make_key(ns, cj, j);
+      P0[j] = __float_as_uint(bcur);
+      P1[j] = __float_as_uint(nb);
+      sm.tsprev[j] = ts_prev;
     }
+    PHASE_MARK(3);
 
-    // ---- phase 4: new children.  Count, scan, then write at deterministic offsets.
-    uint32_t n_new_total = 0;
-    {
-      uint32_t run_base = n_live;
-      for (uint32_t base = 0; base < n_live; base += NT) {
-        const uint32_t i = base + tid;
-        uint32_t cnt = 0;
-        uint32_t allow = 0;  // bit c set: create child c
-        float si = kNegMax;
-        uint32_t nd = 0;
-        if (i < n_live) {
-          si = L_score[i];
-          nd = L_node[i];
-          if (si != kNegMax) {
-            const uint32_t have = s_child[i];
-            if (p.has_scorer) {
-              const int32_t st = s.dict_state[nd];
-              const uint8_t* srec = sv.blob + sv.fst_states_off + (uint64_t)st * 20;
-              const uint32_t pos = sttscorer::load_u32(srec + 4), narcs = sttscorer::load_u32(srec + 8);
-              const uint8_t* arcs = sv.blob + sv.fst_arcs_off + (uint64_t)pos * 16;
-              for (uint32_t a = 0; a < narcs; ++a) {
-                const int c = (int)sttscorer::load_u32(arcs + (uint64_t)a * 16) - 1;
-                if (c < 0 || c >= blank) continue;
-                if ((have >> c) & 1u) continue;
-                if (full_beam && s_logp[c] + si < min_cutoff) continue;
-                allow |= 1u << c;
-              }
-            } else {
-              for (int c = 0; c < blank; ++c) {
-                if ((have >> c) & 1u) continue;
-                allow |= 1u << c;
-              }
-            }
-            cnt = __popc(allow);
+    // ---- phase 4b: write the new children
+    for (uint32_t i = tid; i < n_live; i += NT) {
+      uint32_t allow = sm.child[i];
+      if (!allow) continue;
+      uint32_t e = n_live + sm.lmq[i];
+      const float si = L.score[i];
+      const float bp = L.b[i];
+      const uint32_t cp = (L.chr[i] == (uint8_t)kRootChar) ? kRootChar : (uint32_t)L.chr[i];
+      const uint32_t mask = L.mask[i], pos = L.pos[i];
+      while (allow) {
+        const int c = __ffs(allow) - 1;
+        allow &= allow - 1;
+        float lp;
+        if ((uint32_t)c == cp) lp = (bp > kNegMax) ? s_logp[c] + bp : kNegMax;
+        else lp = s_logp[c] + si;
+        int32_t nds = 0;
+        if (p.has_scorer) {
+          nds = p.fst_arc2[pos + __popc(mask & ((1u << c) - 1u))].y;
+          if (c == p.space_id) {
+            lp += sm.lmterm[i];
+            lp = (float)((double)lp + sv.beta);
           }
         }
-        // block exclusive scan of cnt
-        uint32_t incl = cnt;
-        const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-          uint32_t v = (lane < NT / 32) ? s_warp[lane] : 0, inc2 = v;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, inc2, d);
-            if (lane >= d) inc2 += o;
-          }
-          if (lane < NT / 32) s_warp[lane] = inc2 - v;
-          if (lane == 31) s_warp[NT / 32] = inc2;
-        }
-        __syncthreads();
-        uint32_t e = run_base + s_warp[warp] + (incl - cnt);
-        const uint32_t round_total = s_warp[NT / 32];
-        __syncthreads();
-        if (cnt && e + cnt <= s.cand_cap) {
-          const uint32_t cp = s.chr[nd];
-          const float bp = L_b[i];
-          const int32_t st = s.dict_state[nd];
-          while (allow) {
-            const int c = __ffs(allow) - 1;
-            allow &= allow - 1;
-            float lp;
-            if ((uint32_t)c == cp) lp = (bp > kNegMax) ? s_logp[c] + bp : kNegMax;
-            else lp = s_logp[c] + si;
-            int32_t nds = 0;
-            uint32_t wid = 0;
-            if (p.has_scorer) {
-              const int32_t nxt = sttscorer::fst_find(sv, st, c + 1);
-              nds = sttscorer::fst_is_final(sv, nxt) ? (int32_t)sv.fst_start : nxt;
-              if (c == p.space_id) {
-                lp += s.lm_term[i];
-                lp = (float)((double)lp + sv.beta);
-                wid = s.lm_word[i];
-              }
-            }
-            s.c_score[e] = lp;
-            s.c_a[e] = i;
-            s.c_b[e] = (uint32_t)c;
-            s.c_c[e] = (uint32_t)nds;
-            s.c_d[e] = wid;
-            s.c_key[e] = ((uint64_t)sortable(lp) << 32) | ((uint64_t)(255u - (uint32_t)c) << 24) |
-                         (uint64_t)(0xffffffu - (e & 0xffffffu));
-            ++e;
-          }
-        }
-        run_base += round_total;
+        K[e] = make_key(lp, (uint32_t)c, e);
+        P0[e] = i | ((uint32_t)c << 16);
+        P1[e] = (uint32_t)nds;
+        ++e;
       }
-      n_new_total = run_base - n_live;
     }
     __syncthreads();
-    const uint32_t N = n_live + n_new_total;
-    if (N > s.cand_cap) { overflow = 1; if (tid == 0) s.scalars[6] = 1; __syncthreads(); continue; }
+    PHASE_MARK(4);
 
     // ---- phase 5: exact top-W radix select on the 64-bit key (:263-274 nth_element + prefix_compare)
-    uint64_t sel_prefix = 0, sel_mask = 0;
+    unsigned long long sel_prefix = 0, sel_mask = 0;
     if (N > (uint32_t)W) {
       uint32_t k_rem = (uint32_t)W;
       for (int pass = 7; pass >= 0; --pass) {
@@ -531,7 +654,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         for (int h = tid; h < 256; h += NT) s_hist[h] = 0;
         __syncthreads();
         for (uint32_t e = tid; e < N; e += NT) {
-          const uint64_t key = s.c_key[e];
+          const unsigned long long key = K[e];
           if ((key & sel_mask) == sel_prefix) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -562,91 +685,110 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           }
         }
         __syncthreads();
-        sel_prefix |= (uint64_t)s_u[2] << shift;
-        sel_mask |= (uint64_t)255u << shift;
+        sel_prefix |= (unsigned long long)s_u[2] << shift;
+        sel_mask |= (unsigned long long)255u << shift;
         k_rem = s_u[3];
         const bool done = (s_u[4] == k_rem);  // every element with this prefix is selected
         __syncthreads();
         if (done) break;
       }
     }
+    PHASE_MARK(5);
 
     // ---- phase 6: order-preserving compaction + commit (iterate_to_vec :159-190, remove :192-209)
-    const uint32_t nsel = sel ^ 1u;
-    float* N_score = s.score[nsel];
-    float* N_b = s.b_prev[nsel];
-    float* N_nb = s.nb_prev[nsel];
-    uint32_t* N_node = s.node[nsel];
-    uint32_t* N_ts = s.ts[nsel];
-    uint32_t out_base = 0;
-    uint32_t n_live_surv = 0;
     if (tid == 0) s_u[5] = arena_count;
+    uint32_t out_base = 0;
     // pass A: live entries (they precede new ones in candidate order)
     for (uint32_t base = 0; base < n_live; base += NT) {
       const uint32_t e = base + tid;
+      unsigned long long key = 0;
       bool keep = false;
-      if (e < n_live) keep = (N <= (uint32_t)W) || ((s.c_key[e] & sel_mask) >= sel_prefix);
-      uint32_t total;
-      const uint32_t pos = out_base + block_scan_flag<NT>(keep, s_warp, total);
       if (e < n_live) {
-        const uint32_t nd = L_node[e];
+        key = K[e];
+        keep = (N <= (uint32_t)W) || ((key & sel_mask) >= sel_prefix);
+      }
+      uint32_t total;
+      const uint32_t pos = out_base + block_scan<NT>(keep ? 1u : 0u, s_warp, total);
+      if (e < n_live) {
+        const uint32_t nd = L.node[e];
         if (keep) {
-          N_score[pos] = s.c_score[e];
-          N_b[pos] = __uint_as_float(s.c_a[e]);
-          N_nb[pos] = __uint_as_float(s.c_b[e]);
-          N_node[pos] = nd;
-          const uint32_t tp = s.c_c[e];
+          Nx.score[pos] = unsortable((uint32_t)(key >> 32));
+          Nx.b[pos] = __uint_as_float(P0[e]);
+          Nx.nb[pos] = __uint_as_float(P1[e]);
+          Nx.node[pos] = nd;
+          Nx.pnode[pos] = L.pnode[e];
+          Nx.lsp[pos] = L.lsp[e];
+          Nx.pos[pos] = L.pos[e];
+          Nx.mask[pos] = L.mask[e];
+          Nx.dict[pos] = L.dict[e];
+          Nx.chr[pos] = L.chr[e];
+          const uint32_t tp = sm.tsprev[e];
           if (tp != kNone) {
             const uint32_t id = ts_count + pos;
             if (id < s.ts_cap) { s.ts_parent[id] = tp; s.ts_val[id] = abs_t; }
-            N_ts[pos] = id;
+            Nx.ts[pos] = id;
           } else {
-            N_ts[pos] = L_ts[e];
+            Nx.ts[pos] = L.ts[e];
           }
-          s.live_slot[nd] = pos;
+          s.nodes[nd].live_slot = pos;
         } else {
-          s.live_slot[nd] = kNone;
+          s.nodes[nd].live_slot = kNone;
         }
       }
       out_base += total;
     }
-    n_live_surv = out_base;
+    const uint32_t n_live_surv = out_base;
     // pass B: new entries
     for (uint32_t base = n_live; base < N; base += NT) {
       const uint32_t e = base + tid;
+      unsigned long long key = 0;
       bool keep = false;
-      if (e < N) keep = (N <= (uint32_t)W) || ((s.c_key[e] & sel_mask) >= sel_prefix);
+      if (e < N) {
+        key = K[e];
+        keep = (N <= (uint32_t)W) || ((key & sel_mask) >= sel_prefix);
+      }
       uint32_t total;
-      const uint32_t pos = out_base + block_scan_flag<NT>(keep, s_warp, total);
+      const uint32_t pos = out_base + block_scan<NT>(keep ? 1u : 0u, s_warp, total);
       if (e < N && keep) {
-        const uint32_t pi = s.c_a[e];
-        const uint32_t c = s.c_b[e];
-        const float lp = s.c_score[e];
-        const uint32_t pnode = L_node[pi];
+        const uint32_t pk = P0[e];
+        const uint32_t pi = pk & 0xffffu, c = pk >> 16;
+        const int32_t nds = (int32_t)P1[e];
+        const float lp = unsortable((uint32_t)(key >> 32));
+        const uint32_t pnode = L.node[pi];
         const unsigned long long hk = ht_make_key(pnode, c);
         uint32_t id = ht_find(s, hk);
+        const bool is_space = ((int)c == p.space_id);
         if (id == kNone) {
           id = atomicAdd(&s_u[5], 1u);  // fresh arena node
           if (id < s.arena_cap) {
-            s.parent[id] = pnode;
-            s.chr[id] = c;
-            s.dict_state[id] = (int32_t)s.c_c[e];
-            s.last_space[id] = ((int)c == p.space_id) ? id : s.last_space[pnode];
-            s.word_id[id] = s.c_d[e];
+            Node n;
+            n.parent = pnode; n.chr = c; n.dict = nds; n.last_space = is_space ? id : L.lsp[pi];
+            n.word_id = (is_space && p.has_scorer) ? sm.lmwid[pi] : 0u;
+            n.live_slot = pos; n.lm_wid = kNone; n.pad = 0;
+            s.nodes[id] = n;
             ht_insert(s, hk, id);
           }
+        } else {
+          s.nodes[id].live_slot = pos;  // revived under its old identity
         }
-        if (id < s.arena_cap) s.live_slot[id] = pos;
-        N_score[pos] = lp;
-        N_b[pos] = kNegMax;
-        N_nb[pos] = lp;
-        N_node[pos] = id;
+        Nx.score[pos] = lp;
+        Nx.b[pos] = kNegMax;
+        Nx.nb[pos] = lp;
+        Nx.node[pos] = id;
+        Nx.pnode[pos] = pnode;
+        Nx.lsp[pos] = is_space ? id : L.lsp[pi];
+        Nx.dict[pos] = nds;
+        Nx.chr[pos] = (uint8_t)c;
+        uint2 st = make_uint2(0u, all_labels);
+        if (p.has_scorer) st = p.fst_state2[nds];
+        Nx.pos[pos] = st.x;
+        Nx.mask[pos] = st.y;
         if (lp > kNegMax) {  // "prefix_new->log_prob_nb_cur < log_p" (:246-251)
           const uint32_t tid2 = ts_count + pos;
-          if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L_ts[pi]; s.ts_val[tid2] = abs_t; }
-          N_ts[pos] = tid2;
+          if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L.ts[pi]; s.ts_val[tid2] = abs_t; }
+          Nx.ts[pos] = tid2;
         } else {
-          N_ts[pos] = kNone;
+          Nx.ts[pos] = kNone;
         }
       }
       out_base += total;
@@ -657,21 +799,36 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     ts_count += n_surv;
     if (arena_count > s.arena_cap || ts_count > s.ts_cap) overflow = 1;
     n_live = n_surv;
-    sel = nsel;
-    __threadfence_block();
-    __syncthreads();
+    (void)n_live_surv;
+    cur ^= 1;
+    PHASE_MARK(6);
   }
+#undef PHASE_MARK
 
+  // ---- store the live list for the next launch / finalize
+  __syncthreads();
+  {
+    const LiveList<WC>& L = sm.live[cur];
+    for (uint32_t i = tid; i < n_live; i += NT) {
+      s.score[i] = L.score[i];
+      s.b_prev[i] = L.b[i];
+      s.nb_prev[i] = L.nb[i];
+      s.node[i] = L.node[i];
+      s.ts[i] = L.ts[i];
+    }
+  }
   if (tid == 0) {
     s.scalars[0] = n_live;
-    s.scalars[1] = sel;
     s.scalars[2] = arena_count;
     s.scalars[3] = ts_count;
     s.scalars[4] = abs_t;
     s.scalars[5] = start_expanding;
     s.scalars[6] = overflow;
-    s.scalars[7] += s_u[6];   // words scored by the LM in this launch
+    s.scalars[7] += s_u[6];   // words scored by the LM (reference-equivalent window sizes)
     s.scalars[8] += s_u[7];   // LM calls
+    if (max_cand > s.scalars[9]) s.scalars[9] = max_cand;
+    s.scalars[10] += spills;
+    for (int q = 0; q < 8; ++q) s.phase_cycles[q] += s_ph[q];
   }
 }
 
@@ -693,25 +850,22 @@ __global__ void __launch_bounds__(NT) decoder_finalize_kernel(Slot* slots, const
   const FinalOut o = outs[blockIdx.x];
   const int tid = threadIdx.x;
   const uint32_t n_live = s.scalars[0];
-  const uint32_t sel = s.scalars[1];
-  const float* L_score = s.score[sel];
-  const uint32_t* L_node = s.node[sel];
-  const uint32_t* L_ts = s.ts[sel];
   __shared__ unsigned long long s_best[NT / 32];
-  __shared__ unsigned long long s_pick;
+  float* f_score = reinterpret_cast<float*>(s.c_p0);  // scratch (the live list itself is left untouched:
+  unsigned long long* f_key = s.c_key;                //          IntermediateDecode is const)
 
-  // final scores -> c_score, keys -> c_key (live list itself is left untouched: IntermediateDecode is const)
   for (uint32_t i = tid; i < n_live; i += NT) {
-    const uint32_t nd = L_node[i];
-    float sc = L_score[i];
-    const uint32_t c = s.chr[nd];
+    const uint32_t nd = s.node[i];
+    float sc = s.score[i];
+    const uint32_t c = s.nodes[nd].chr;
     if (p.has_scorer && i < (uint32_t)p.beam && c != kRootChar && (int)c != p.space_id) {
-      float add = lm_final_term(s, p.scorer, nd);
+      uint32_t wid_unused, nw_unused;
+      float add = (float)(lm_eval_node(s, p.scorer, nd, &wid_unused, &nw_unused) * p.scorer.alpha);
       add = (float)((double)add + p.scorer.beta);
       sc = sc + add;
     }
-    s.c_score[i] = sc;
-    s.c_key[i] = ((uint64_t)sortable(sc) << 32) | ((uint64_t)(255u - c) << 24) | (uint64_t)(0xffffffu - i);
+    f_score[i] = sc;
+    f_key[i] = make_key(sc, c, i);
   }
   __syncthreads();
   int n_ret = (int)n_live < num_results ? (int)n_live : num_results;
@@ -719,7 +873,7 @@ __global__ void __launch_bounds__(NT) decoder_finalize_kernel(Slot* slots, const
   for (int r = 0; r < n_ret; ++r) {
     unsigned long long best = 0;
     for (uint32_t i = tid; i < n_live; i += NT) {
-      const unsigned long long k = s.c_key[i];
+      const unsigned long long k = f_key[i];
       if (k > best) best = k;
     }
 #pragma unroll
@@ -732,21 +886,20 @@ __global__ void __launch_bounds__(NT) decoder_finalize_kernel(Slot* slots, const
     if (tid == 0) {
       unsigned long long b = s_best[0];
       for (int w = 1; w < NT / 32; ++w) if (s_best[w] > b) b = s_best[w];
-      s_pick = b;
       const uint32_t i = 0xffffffu - (uint32_t)(b & 0xffffffu);
-      s.c_key[i] = 0;  // remove from further rounds
+      f_key[i] = 0;  // remove from further rounds
       // backtrack tokens (get_path_vec) and timesteps (get_history)
-      uint32_t nd = L_node[i];
+      const uint32_t nd = s.node[i];
       int len = 0;
-      for (uint32_t w = nd; s.chr[w] != kRootChar; w = s.parent[w]) ++len;
+      for (uint32_t w = nd; s.nodes[w].chr != kRootChar; w = s.nodes[w].parent) ++len;
       o.n_tokens[r] = len;
-      o.confidence[r] = (double)s.c_score[i];
+      o.confidence[r] = (double)f_score[i];
       int k = len;
-      for (uint32_t w = nd; s.chr[w] != kRootChar; w = s.parent[w]) {
+      for (uint32_t w = nd; s.nodes[w].chr != kRootChar; w = s.nodes[w].parent) {
         --k;
-        if (k < o.max_tokens) o.tokens[(size_t)r * o.max_tokens + k] = s.chr[w];
+        if (k < o.max_tokens) o.tokens[(size_t)r * o.max_tokens + k] = s.nodes[w].chr;
       }
-      uint32_t tn = L_ts[i];
+      const uint32_t tn = s.ts[i];
       int tlen = 0;
       for (uint32_t w = tn; w != kNone && w != 0; w = s.ts_parent[w]) ++tlen;
       k = tlen;

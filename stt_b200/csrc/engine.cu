@@ -140,6 +140,8 @@ struct Engine {
   bool has_scorer = false;
   uint8_t* scorer_blob = nullptr;
   sttscorer::ScorerView scorer_view{};
+  uint2* fst_state2 = nullptr;  // per state {first arc, label mask}
+  int2* fst_arc2 = nullptr;     // per arc {ilabel, child dictionary state}
 };
 
 const sttmodel::HostModel& engine_model(const Engine* e) { return e->hm; }
@@ -322,7 +324,11 @@ Engine* engine_create(const sttmodel::HostModel& m, std::string* err) {
 
 void engine_clear_scorer(Engine* e) {
   if (e->scorer_blob) cudaFree(e->scorer_blob);
+  if (e->fst_state2) cudaFree(e->fst_state2);
+  if (e->fst_arc2) cudaFree(e->fst_arc2);
   e->scorer_blob = nullptr;
+  e->fst_state2 = nullptr;
+  e->fst_arc2 = nullptr;
   e->has_scorer = false;
 }
 
@@ -348,6 +354,41 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
   if (cudaMalloc(reinterpret_cast<void**>(&e->scorer_blob), n + 16) != cudaSuccess) return sttscorer::SCORER_UNREADABLE;
   cudaMemset(e->scorer_blob + n, 0, 16);
   if (cudaMemcpy(e->scorer_blob, bytes, n, cudaMemcpyHostToDevice) != cudaSuccess) return sttscorer::SCORER_UNREADABLE;
+  // Pre-digest the dictionary FST for the decoder (semantics of PathTrie::get_path_trie, path_trie.cpp:60-88):
+  // per state the set of labels with an outgoing arc, per arc the child's dictionary state, i.e. Start() when the
+  // arc's target is final ("restart spell checker at the start state"), else the target.
+  {
+    v.blob = bytes;  // host view for the preprocessing
+    std::vector<uint2> st2((size_t)v.fst_nstates);
+    std::vector<int2> ar2((size_t)v.fst_narcs);
+    for (int64_t q = 0; q < v.fst_nstates; ++q) {
+      const uint8_t* srec = bytes + v.fst_states_off + (uint64_t)q * 20;
+      uint32_t pos, narcs;
+      memcpy(&pos, srec + 4, 4);
+      memcpy(&narcs, srec + 8, 4);
+      uint32_t mask = 0;
+      for (uint32_t a = 0; a < narcs; ++a) {
+        const uint8_t* arc = bytes + v.fst_arcs_off + (uint64_t)(pos + a) * 16;
+        int32_t il, nx;
+        memcpy(&il, arc, 4);
+        memcpy(&nx, arc + 12, 4);
+        if (il >= 1 && il <= 32) mask |= 1u << (il - 1);
+        if (a > 0) {
+          int32_t prev;
+          memcpy(&prev, arc - 16, 4);
+          if (prev >= il) return sttscorer::SCORER_INVALID_TRIE;  // SortedMatcher needs ilabel-sorted, deterministic arcs
+        }
+        const bool fin = sttscorer::fst_is_final(v, nx);
+        ar2[pos + a] = make_int2(il, fin ? (int32_t)v.fst_start : nx);
+      }
+      st2[(size_t)q] = make_uint2(pos, mask);
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&e->fst_state2), std::max<size_t>(st2.size(), 1) * sizeof(uint2)) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&e->fst_arc2), std::max<size_t>(ar2.size(), 1) * sizeof(int2)) != cudaSuccess)
+      return sttscorer::SCORER_UNREADABLE;
+    cudaMemcpy(e->fst_state2, st2.data(), st2.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+    cudaMemcpy(e->fst_arc2, ar2.data(), ar2.size() * sizeof(int2), cudaMemcpyHostToDevice);
+  }
   v.blob = e->scorer_blob;
   e->scorer_view = v;
   e->has_scorer = true;
@@ -424,38 +465,31 @@ int alloc_slots(Batch* b) {
     off = align_up(off + bytes, 256);
     return o;
   };
-  struct Offs {
-    size_t parent, chr, dict, lsp, wid, lslot, htk, htv, tsp, tsv, score[2], bp[2], nbp[2], node[2], ts[2], cs, ca, cb, cc,
-        cd, ck, lmt, lmw, scal;
-  } o;
-  o.parent = take(4ull * arena_cap); o.chr = take(4ull * arena_cap); o.dict = take(4ull * arena_cap);
-  o.lsp = take(4ull * arena_cap); o.wid = take(4ull * arena_cap); o.lslot = take(4ull * arena_cap);
-  o.htk = take(8ull * ht); o.htv = take(4ull * ht);
-  o.tsp = take(4ull * ts_cap); o.tsv = take(4ull * ts_cap);
-  for (int k = 0; k < 2; ++k) {
-    o.score[k] = take(4ull * W); o.bp[k] = take(4ull * W); o.nbp[k] = take(4ull * W);
-    o.node[k] = take(4ull * W); o.ts[k] = take(4ull * W);
-  }
-  o.cs = take(4ull * cand_cap); o.ca = take(4ull * cand_cap); o.cb = take(4ull * cand_cap);
-  o.cc = take(4ull * cand_cap); o.cd = take(4ull * cand_cap); o.ck = take(8ull * cand_cap);
-  o.lmt = take(4ull * W); o.lmw = take(4ull * W); o.scal = take(64);
+  const int SW = sttdec::kStateWords;
+  const size_t o_nodes = take(sizeof(sttdec::Node) * (size_t)arena_cap);
+  const size_t o_ht = take(sizeof(sttdec::HtSlot) * (size_t)ht);
+  const size_t o_lmc = take(8ull * arena_cap), o_lmsw = take(4ull * arena_cap * SW), o_lmsb = take(4ull * arena_cap * SW);
+  const size_t o_lmm = take(4ull * arena_cap);
+  const size_t o_tsp = take(4ull * ts_cap), o_tsv = take(4ull * ts_cap);
+  const size_t o_sc = take(4ull * W), o_bp = take(4ull * W), o_nb = take(4ull * W), o_nd = take(4ull * W), o_lts = take(4ull * W);
+  const size_t o_ck = take(8ull * cand_cap), o_p0 = take(4ull * cand_cap), o_p1 = take(4ull * cand_cap);
+  const size_t o_scal = take(64), o_ph = take(64);
   b->slot_bytes = off;
   CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_slot_mem), b->slot_bytes * b->B_cap));
   b->h_slots.resize(b->B_cap);
   for (int u = 0; u < b->B_cap; ++u) {
     uint8_t* base = b->d_slot_mem + b->slot_bytes * u;
     sttdec::Slot& s = b->h_slots[u];
-    s.parent = (uint32_t*)(base + o.parent); s.chr = (uint32_t*)(base + o.chr); s.dict_state = (int32_t*)(base + o.dict);
-    s.last_space = (uint32_t*)(base + o.lsp); s.word_id = (uint32_t*)(base + o.wid); s.live_slot = (uint32_t*)(base + o.lslot);
-    s.ht_key = (unsigned long long*)(base + o.htk); s.ht_val = (uint32_t*)(base + o.htv); s.ht_mask = ht - 1;
-    s.ts_parent = (uint32_t*)(base + o.tsp); s.ts_val = (uint32_t*)(base + o.tsv);
-    for (int k = 0; k < 2; ++k) {
-      s.score[k] = (float*)(base + o.score[k]); s.b_prev[k] = (float*)(base + o.bp[k]); s.nb_prev[k] = (float*)(base + o.nbp[k]);
-      s.node[k] = (uint32_t*)(base + o.node[k]); s.ts[k] = (uint32_t*)(base + o.ts[k]);
-    }
-    s.c_score = (float*)(base + o.cs); s.c_a = (uint32_t*)(base + o.ca); s.c_b = (uint32_t*)(base + o.cb);
-    s.c_c = (uint32_t*)(base + o.cc); s.c_d = (uint32_t*)(base + o.cd); s.c_key = (uint64_t*)(base + o.ck);
-    s.lm_term = (float*)(base + o.lmt); s.lm_word = (uint32_t*)(base + o.lmw); s.scalars = (uint32_t*)(base + o.scal);
+    s.nodes = (sttdec::Node*)(base + o_nodes);
+    s.ht = (sttdec::HtSlot*)(base + o_ht);
+    s.ht_mask = ht - 1;
+    s.lm_cond = (double*)(base + o_lmc); s.lm_sw = (uint32_t*)(base + o_lmsw); s.lm_sb = (float*)(base + o_lmsb);
+    s.lm_meta = (uint32_t*)(base + o_lmm);
+    s.ts_parent = (uint32_t*)(base + o_tsp); s.ts_val = (uint32_t*)(base + o_tsv);
+    s.score = (float*)(base + o_sc); s.b_prev = (float*)(base + o_bp); s.nb_prev = (float*)(base + o_nb);
+    s.node = (uint32_t*)(base + o_nd); s.ts = (uint32_t*)(base + o_lts);
+    s.c_key = (unsigned long long*)(base + o_ck); s.c_p0 = (uint32_t*)(base + o_p0); s.c_p1 = (uint32_t*)(base + o_p1);
+    s.scalars = (uint32_t*)(base + o_scal); s.phase_cycles = (unsigned long long*)(base + o_ph);
     s.arena_cap = arena_cap; s.ts_cap = ts_cap; s.beam_cap = W; s.cand_cap = cand_cap;
   }
   CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_slots), sizeof(sttdec::Slot) * b->B_cap));
@@ -722,6 +756,8 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
   dp.space_id = (int)e->hm.space_label;
   dp.has_scorer = e->has_scorer ? 1 : 0;
   if (e->has_scorer) dp.scorer = e->scorer_view;
+  dp.fst_state2 = e->fst_state2;
+  dp.fst_arc2 = e->fst_arc2;
   return dp;
 }
 
@@ -729,7 +765,7 @@ int decoder_reset(Batch* b, int n_slots) {
   cudaStream_t st = b->st;
   // hash tables must start empty
   for (int u = 0; u < n_slots; ++u)
-    CUDA_OK(cudaMemsetAsync(b->h_slots[u].ht_key, 0, 8ull * (b->h_slots[u].ht_mask + 1), st));
+    CUDA_OK(cudaMemsetAsync(b->h_slots[u].ht, 0, sizeof(sttdec::HtSlot) * ((size_t)b->h_slots[u].ht_mask + 1), st));
   const int32_t fst_start = b->e->has_scorer ? (int32_t)b->e->scorer_view.fst_start : 0;
   sttdec::decoder_init_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b->d_slots, n_slots, fst_start);
   CUDA_OK(cudaGetLastError());
@@ -742,8 +778,22 @@ int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& i
   CUDA_OK(cudaMemcpyAsync(b->d_inputs, in.data(), sizeof(sttdec::StepInput) * n_slots, cudaMemcpyHostToDevice, st));
   const sttdec::DecodeParams dp = make_decode_params(b, beam);
   constexpr int NT = 512;
-  const size_t dyn = 8ull * b->beam_cap;
-  sttdec::decoder_step_kernel<NT><<<n_slots, NT, dyn, st>>>(b->d_slots, b->d_inputs, dp);
+  if (b->beam_cap <= 512) {
+    using SM = sttdec::StepSmem<512, 3072>;
+    auto kern = sttdec::decoder_step_kernel<NT, 512, 3072>;
+    static bool cfg = false;
+    if (!cfg) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM))); cfg = true; }
+    kern<<<n_slots, NT, sizeof(SM), st>>>(b->d_slots, b->d_inputs, dp);
+  } else if (b->beam_cap <= 2048) {
+    using SM = sttdec::StepSmem<2048, 0>;
+    auto kern = sttdec::decoder_step_kernel<NT, 2048, 0>;
+    static bool cfg = false;
+    if (!cfg) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM))); cfg = true; }
+    kern<<<n_slots, NT, sizeof(SM), st>>>(b->d_slots, b->d_inputs, dp);
+  } else {
+    fprintf(stderr, "[stt_b200] beam widths above 2048 are not supported by the shared-memory decoder\n");
+    return -1;
+  }
   CUDA_OK(cudaGetLastError());
   b->launches += 1;
   return 0;
@@ -853,6 +903,16 @@ int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out) {
   }
   out->resize(b->B);
   for (int u = 0; u < b->B; ++u) parse_results(b, b->h_out_mem + b->out_bytes_per_utt * u, &(*out)[u]);
+  return 0;
+}
+
+int batch_phase_cycles(Batch* b, unsigned long long* out8) {
+  for (int q = 0; q < 8; ++q) out8[q] = 0;
+  for (int u = 0; u < b->B; ++u) {
+    unsigned long long ph[8];
+    CUDA_OK(cudaMemcpy(ph, b->h_slots[u].phase_cycles, sizeof(ph), cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 8; ++q) out8[q] += ph[q];
+  }
   return 0;
 }
 

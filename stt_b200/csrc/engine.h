@@ -46,6 +46,7 @@ int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out);
 const StageTimes& batch_times(const Batch* b);
 long long batch_kernel_launches(const Batch* b);
 // Debug / test access
+int batch_phase_cycles(Batch* b, unsigned long long* out8);  // instrumentation: summed over utterances
 int batch_lm_stats(Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls);  // instrumentation
 int batch_T(const Batch* b, int utt);                        // timesteps of utterance `utt` after upload
 int batch_copy_features(Batch* b, int utt, float* out);      // [T, n_input] fp32 MFCC
