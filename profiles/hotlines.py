@@ -37,7 +37,7 @@ for l in sass[start + 1:]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/", l)
     if m:
         off2line[int(m.group(1), 16)] = cur
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern.split("ILi")[0]], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hi = [i for i, r in enumerate(rows) if "Address" in r and "# Samples" in r][0]
 h = rows[hi]

@@ -388,7 +388,9 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   const sttscorer::ScorerView& sv = p.scorer;
   const uint32_t all_labels = (blank >= 32) ? 0xffffffffu : ((1u << blank) - 1u);
 
-  __shared__ float s_logp[kMaxClasses];
+  __shared__ float s_logp2[2][kMaxClasses];
+  __shared__ double s_logblank[2];
+  __shared__ uint32_t s_gate[2];
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_warp[NT / 32 + 1];
   __shared__ float s_red[NT / 32];
@@ -429,6 +431,17 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     L.pos[i] = st.x;
     L.mask[i] = st.y;
   }
+  for (uint32_t i = tid; i < (uint32_t)WC; i += NT) sm.child[i] = 0;
+  if (in.n_steps > 0) {
+    // class log-probs of the first row (get_pruned_emissions :328-358 with the C-API's cutoff_prob = 1.0,
+    // cutoff_top_n = 40 >= n_classes: no pruning, index order, blank last); later rows are prepared one step ahead
+    if (tid < C) s_logp2[0][tid] = sttmath::glibc_logf(in.probs[tid] + kFltMin);
+    if (tid == 0) {
+      const double pb = (double)in.probs[blank];
+      s_gate[0] = pb < 0.999 ? 1u : 0u;
+      s_logblank[0] = log(pb);
+    }
+  }
   __syncthreads();
   long long ph_t0 = clock64();
 #define PHASE_MARK(k) do { if (tid == 0) { const long long _t = clock64(); s_ph[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
@@ -437,13 +450,24 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     const float* prob = in.probs + (size_t)step * C;
     LiveList<WC>& L = sm.live[cur];
     LiveList<WC>& Nx = sm.live[cur ^ 1];
-    // ---- phase 0: gate (:125-132), class log-probs (get_pruned_emissions :328-358 with the C-API's cutoff_prob = 1.0,
-    //      cutoff_top_n = 40 >= n_classes: no pruning, index order, blank last) and the beam's minimum score
-    if (tid < C) s_logp[tid] = sttmath::glibc_logf(prob[tid] + kFltMin);
-    if (tid == 0) {
-      if ((double)prob[blank] < 0.999) start_expanding = 1;
-      s_u[0] = start_expanding;
-      s_u[1] = 0;  // LM queue length
+    // ---- phase 0: gate (:125-132), the beam's minimum score, and which (parent, label) pairs already have a live
+    //      child.  This row's log-probs were prepared during the previous step; the next row is fetched now and turned
+    //      into log-probs at the end of this step, off the critical path.
+    const int cb = step & 1;
+    const float* s_logp = s_logp2[cb];
+    float next_p = 0.f;
+    const bool have_next = (step + 1 < in.n_steps);
+    if (have_next && tid < C) next_p = prob[C + tid];
+    if (start_expanding | s_gate[cb]) {
+      for (uint32_t j = tid; j < n_live; j += NT) {
+        const uint32_t pn = L.pnode[j];
+        uint32_t pi = kNone;
+        if (pn != kNone) {
+          pi = s.nodes[pn].live_slot;
+          if (pi != kNone) atomicOr(&sm.child[pi], 1u << L.chr[j]);
+        }
+        sm.plive[j] = pi;
+      }
     }
     {
       float m = 3.402823466e+38f;
@@ -452,10 +476,21 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
       if ((tid & 31) == 0) s_red[tid >> 5] = m;
     }
-    for (uint32_t i = tid; i < n_live; i += NT) sm.child[i] = 0;
+    if (tid == 0) s_u[1] = 0;  // LM queue length
+    start_expanding |= s_gate[cb];
     __syncthreads();
-    start_expanding = s_u[0];
-    if (!start_expanding || overflow) { __syncthreads(); continue; }
+    if (!start_expanding || overflow) {
+      if (have_next) {
+        if (tid < C) s_logp2[cb ^ 1][tid] = sttmath::glibc_logf(next_p + kFltMin);
+        if (tid == 0) {
+          const double pb = (double)prob[C + blank];
+          s_gate[cb ^ 1] = pb < 0.999 ? 1u : 0u;
+          s_logblank[cb ^ 1] = log(pb);
+        }
+      }
+      __syncthreads();
+      continue;
+    }
     // min_cutoff (:134-146), computed redundantly by every thread to save a barrier
     float min_cutoff = kNegMax;
     bool full_beam = false;
@@ -464,22 +499,10 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
 #pragma unroll
       for (int w = 1; w < NT / 32; ++w) mm = fminf(mm, s_red[w]);
       const double beta_pos = sv.beta > 0.0 ? sv.beta : 0.0;
-      min_cutoff = (float)((double)mm + log((double)prob[blank]) - beta_pos);
+      min_cutoff = (float)((double)mm + s_logblank[cb] - beta_pos);
       full_beam = (n_live == (uint32_t)W);
     }
     PHASE_MARK(0);
-
-    // ---- phase 2: which (parent, label) pairs already have a live child
-    for (uint32_t j = tid; j < n_live; j += NT) {
-      const uint32_t pn = L.pnode[j];
-      uint32_t pi = kNone;
-      if (pn != kNone) {
-        pi = s.nodes[pn].live_slot;
-        if (pi != kNone) atomicOr(&sm.child[pi], 1u << L.chr[j]);
-      }
-      sm.plive[j] = pi;
-    }
-    __syncthreads();
     PHASE_MARK(1);
 
     // ---- phase 2b: LM terms of the live prefixes that will be extended by the space this step
@@ -643,6 +666,15 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       }
     }
     __syncthreads();
+    for (uint32_t i = tid; i < (uint32_t)WC; i += NT) sm.child[i] = 0;  // ready for the next step's phase 0
+    if (have_next) {
+      if (tid < C) s_logp2[cb ^ 1][tid] = sttmath::glibc_logf(next_p + kFltMin);
+      if (tid == NT - 1) {
+        const double pb = (double)prob[C + blank];
+        s_gate[cb ^ 1] = pb < 0.999 ? 1u : 0u;
+        s_logblank[cb ^ 1] = log(pb);
+      }
+    }
     PHASE_MARK(4);
 
     // ---- phase 5: exact top-W radix select on the 64-bit key (:263-274 nth_element + prefix_compare)
@@ -697,13 +729,14 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
 
     // ---- phase 6: order-preserving compaction + commit (iterate_to_vec :159-190, remove :192-209)
     if (tid == 0) s_u[5] = arena_count;
+    // (i) shared-memory-only compaction, in candidate order (live entries precede new ones): survivors get their slot
+    //     in the next live list; a new survivor parks (parent index, label, dictionary state) there.
     uint32_t out_base = 0;
-    // pass A: live entries (they precede new ones in candidate order)
-    for (uint32_t base = 0; base < n_live; base += NT) {
+    for (uint32_t base = 0; base < N; base += NT) {
       const uint32_t e = base + tid;
       unsigned long long key = 0;
       bool keep = false;
-      if (e < n_live) {
+      if (e < N) {
         key = K[e];
         keep = (N <= (uint32_t)W) || ((key & sel_mask) >= sel_prefix);
       }
@@ -731,67 +764,61 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
             Nx.ts[pos] = L.ts[e];
           }
           s.nodes[nd].live_slot = pos;
+          sm.lmq[pos] = kNone;  // not a new node
         } else {
           s.nodes[nd].live_slot = kNone;
         }
-      }
-      out_base += total;
-    }
-    const uint32_t n_live_surv = out_base;
-    // pass B: new entries
-    for (uint32_t base = n_live; base < N; base += NT) {
-      const uint32_t e = base + tid;
-      unsigned long long key = 0;
-      bool keep = false;
-      if (e < N) {
-        key = K[e];
-        keep = (N <= (uint32_t)W) || ((key & sel_mask) >= sel_prefix);
-      }
-      uint32_t total;
-      const uint32_t pos = out_base + block_scan<NT>(keep ? 1u : 0u, s_warp, total);
-      if (e < N && keep) {
-        const uint32_t pk = P0[e];
-        const uint32_t pi = pk & 0xffffu, c = pk >> 16;
-        const int32_t nds = (int32_t)P1[e];
+      } else if (e < N && keep) {
         const float lp = unsortable((uint32_t)(key >> 32));
-        const uint32_t pnode = L.node[pi];
-        const unsigned long long hk = ht_make_key(pnode, c);
-        uint32_t id = ht_find(s, hk);
-        const bool is_space = ((int)c == p.space_id);
-        if (id == kNone) {
-          id = atomicAdd(&s_u[5], 1u);  // fresh arena node
-          if (id < s.arena_cap) {
-            Node n;
-            n.parent = pnode; n.chr = c; n.dict = nds; n.last_space = is_space ? id : L.lsp[pi];
-            n.word_id = (is_space && p.has_scorer) ? sm.lmwid[pi] : 0u;
-            n.live_slot = pos; n.lm_wid = kNone; n.pad = 0;
-            s.nodes[id] = n;
-            ht_insert(s, hk, id);
-          }
-        } else {
-          s.nodes[id].live_slot = pos;  // revived under its old identity
-        }
         Nx.score[pos] = lp;
         Nx.b[pos] = kNegMax;
         Nx.nb[pos] = lp;
-        Nx.node[pos] = id;
-        Nx.pnode[pos] = pnode;
-        Nx.lsp[pos] = is_space ? id : L.lsp[pi];
-        Nx.dict[pos] = nds;
-        Nx.chr[pos] = (uint8_t)c;
-        uint2 st = make_uint2(0u, all_labels);
-        if (p.has_scorer) st = p.fst_state2[nds];
-        Nx.pos[pos] = st.x;
-        Nx.mask[pos] = st.y;
-        if (lp > kNegMax) {  // "prefix_new->log_prob_nb_cur < log_p" (:246-251)
-          const uint32_t tid2 = ts_count + pos;
-          if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L.ts[pi]; s.ts_val[tid2] = abs_t; }
-          Nx.ts[pos] = tid2;
-        } else {
-          Nx.ts[pos] = kNone;
-        }
+        Nx.dict[pos] = (int32_t)P1[e];
+        sm.lmq[pos] = P0[e];  // parent live index | label << 16
       }
       out_base += total;
+    }
+    __syncthreads();
+    // (ii) one thread per NEW survivor does the global-memory work (hash lookup / arena node / FST state / timestep
+    //      node), so all those latencies overlap instead of being paid once per 512-candidate round
+    for (uint32_t pos = tid; pos < out_base; pos += NT) {
+      const uint32_t pk = sm.lmq[pos];
+      if (pk == kNone) continue;
+      const uint32_t pi = pk & 0xffffu, c = pk >> 16;
+      const int32_t nds = Nx.dict[pos];
+      const float lp = Nx.score[pos];
+      const uint32_t pnode = L.node[pi];
+      const unsigned long long hk = ht_make_key(pnode, c);
+      uint2 st = make_uint2(0u, all_labels);
+      if (p.has_scorer) st = p.fst_state2[nds];
+      uint32_t id = ht_find(s, hk);
+      const bool is_space = ((int)c == p.space_id);
+      if (id == kNone) {
+        id = atomicAdd(&s_u[5], 1u);  // fresh arena node
+        if (id < s.arena_cap) {
+          Node n;
+          n.parent = pnode; n.chr = c; n.dict = nds; n.last_space = is_space ? id : L.lsp[pi];
+          n.word_id = (is_space && p.has_scorer) ? sm.lmwid[pi] : 0u;
+          n.live_slot = pos; n.lm_wid = kNone; n.pad = 0;
+          s.nodes[id] = n;
+          ht_insert(s, hk, id);
+        }
+      } else {
+        s.nodes[id].live_slot = pos;  // revived under its old identity
+      }
+      Nx.node[pos] = id;
+      Nx.pnode[pos] = pnode;
+      Nx.lsp[pos] = is_space ? id : L.lsp[pi];
+      Nx.chr[pos] = (uint8_t)c;
+      Nx.pos[pos] = st.x;
+      Nx.mask[pos] = st.y;
+      if (lp > kNegMax) {  // "prefix_new->log_prob_nb_cur < log_p" (:246-251)
+        const uint32_t tid2 = ts_count + pos;
+        if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L.ts[pi]; s.ts_val[tid2] = abs_t; }
+        Nx.ts[pos] = tid2;
+      } else {
+        Nx.ts[pos] = kNone;
+      }
     }
     const uint32_t n_surv = out_base;
     __syncthreads();
@@ -799,7 +826,6 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     ts_count += n_surv;
     if (arena_count > s.arena_cap || ts_count > s.ts_cap) overflow = 1;
     n_live = n_surv;
-    (void)n_live_surv;
     cur ^= 1;
     PHASE_MARK(6);
   }

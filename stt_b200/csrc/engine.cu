@@ -625,6 +625,79 @@ int batch_upload(Batch* b, const int16_t* const* pcm, const unsigned* n_samples,
 
 namespace {
 
+
+template <int MT, int STAGES, int CS>
+int launch_lstm_inst(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st, bool probe_only, bool* fits) {
+  using L = sttlstm::SmemLayout<MT, STAGES>;
+  auto kern = sttlstm::lstm_tc_kernel<MT, STAGES, CS>;
+  static bool cfg = false;
+  if (!cfg) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    cfg = true;
+  }
+  cudaLaunchConfig_t cfgl{};
+  cfgl.gridDim = dim3(grid);
+  cfgl.blockDim = dim3(sttlstm::kNumThreads);
+  cfgl.dynamicSmemBytes = L::kTotal;
+  cfgl.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = CS;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfgl.attrs = attrs;
+  cfgl.numAttrs = (CS > 1) ? 2 : 1;
+  if (probe_only) {
+    // all CTAs must be co-resident (device-wide barrier): how many clusters of this size fit at once?
+    int n_clusters = 0;
+    if (CS > 1) {
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfgl) != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
+    } else {
+      int per_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sttlstm::kNumThreads, L::kTotal);
+      n_clusters = per_sm * b->e->num_sms;
+    }
+    *fits = (long long)n_clusters * CS >= grid;
+    return 0;
+  }
+  // A-operand tensor map with a 128/CS-row box (each CTA of a cluster fetches one slice and multicasts it)
+  CUtensorMap tm_h;
+  const size_t rows = (size_t)b->T_cap * b->B_cap + b->B_cap + 256;
+  if (!make_tmap_2d(&tm_h, b->d_hall, rows, b->e->Cp, b->e->Cp, 128 / CS)) return -1;
+  CUDA_OK(cudaLaunchKernelEx(&cfgl, kern, tm_h, b->e->tm_wh, lp));
+  return 0;
+}
+
+template <int MT, int STAGES>
+int launch_lstm_mt(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st) {
+  // largest cluster size that divides the grid AND lets the whole grid be co-resident (GPC sizes vary per part)
+  static int chosen[1024] = {0};  // by grid size
+  int cs = (grid < 1024) ? chosen[grid] : 0;
+  if (cs == 0) {
+    static const char* force = getenv("STT_B200_LSTM_CLUSTER");  // debugging aid: 1 disables multicast
+    const int cap = force ? std::max(1, atoi(force)) : 8;
+    bool fits = false;
+    cs = 1;
+    if (cap >= 8 && grid % 8 == 0 && launch_lstm_inst<MT, STAGES, 8>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 8;
+    else if (cap >= 4 && grid % 4 == 0 && launch_lstm_inst<MT, STAGES, 4>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 4;
+    else if (cap >= 2 && grid % 2 == 0 && launch_lstm_inst<MT, STAGES, 2>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 2;
+    if (grid < 1024) chosen[grid] = cs;
+    if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] LSTM grid %d: cluster size %d\n", grid, cs);
+  }
+  bool unused;
+  if (cs == 8) return launch_lstm_inst<MT, STAGES, 8>(b, lp, grid, st, false, &unused);
+  if (cs == 4) return launch_lstm_inst<MT, STAGES, 4>(b, lp, grid, st, false, &unused);
+  if (cs == 2) return launch_lstm_inst<MT, STAGES, 2>(b, lp, grid, st, false, &unused);
+  return launch_lstm_inst<MT, STAGES, 1>(b, lp, grid, st, false, &unused);
+}
+
+int launch_lstm(Batch* b, const sttlstm::LstmParams& lp, int grid, int B, cudaStream_t st) {
+  if (B <= 128) return launch_lstm_mt<1, 6>(b, lp, grid, st);
+  return launch_lstm_mt<2, 5>(b, lp, grid, st);
+}
+
 // dense 1..3 -> xw -> LSTM -> dense 5,6 + softmax for rows (T timesteps x B utterances); features already in d_feat.
 // probs are written at [b, out_t_offset + t].  LSTM initial state = (d_c, block 0 of d_hall); final state -> d_c, d_h.
 int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
@@ -683,18 +756,7 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
     lp.B = B; lp.T = T; lp.n_cell = Cp; lp.xw = b->d_xw; lp.h_all = b->d_hall; lp.c_state = b->d_c; lp.h_state = b->d_h;
     lp.barrier = b->d_barrier;
     const int grid = Cp / sttlstm::kCellsPerCta;
-    void* args[] = {(void*)&b->tm_hall, (void*)&e->tm_wh, (void*)&lp};
-    if (B <= 128) {
-      using L = sttlstm::SmemLayout<1, 6>;
-      auto kern = sttlstm::lstm_tc_kernel<1, 6>;
-      CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-      CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(sttlstm::kNumThreads), args, L::kTotal, st));
-    } else {
-      using L = sttlstm::SmemLayout<2, 5>;
-      auto kern = sttlstm::lstm_tc_kernel<2, 5>;
-      CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-      CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(sttlstm::kNumThreads), args, L::kTotal, st));
-    }
+    if (launch_lstm(b, lp, grid, B, st)) return -1;
   }
   if (time_it) cudaEventRecord(b->ev[6], st);
   // ---- layer 5 (A = h_1..h_T = rows B.. of h_all) and layer 6 + softmax
@@ -728,8 +790,10 @@ int batch_forward(Batch* b) {
   // grid covers frames_per_utt = T_cap per utterance; blocks beyond an utterance's frame count exit immediately
   {
     sttmfcc::BatchJob j2 = job;
-    const int grid = B * b->T_cap;
-    sttmfcc::mfcc_batch_kernel<<<grid, 256, 0, st>>>(e->tables, j2);
+    const long long items = (long long)B * b->T_cap;
+    const int grid = (int)std::min<long long>((items + sttmfcc::kWarpsPerBlock - 1) / sttmfcc::kWarpsPerBlock,
+                                              (long long)e->num_sms * 5 * 8);
+    sttmfcc::mfcc_batch_kernel<<<grid, sttmfcc::kWarpsPerBlock * 32, 0, st>>>(e->tables, j2, B);
     CUDA_OK(cudaGetLastError());
     b->launches += 1;
   }
@@ -989,7 +1053,8 @@ int batch_stream_push_windows(Batch* b, const int16_t* windows, const int* n_val
       jobs[i].out_f16 = b->d_feat + (size_t)(b->stream_frames + i) * sttmfcc::kFeatLanes;
     }
     CUDA_OK(cudaMemcpyAsync(b->d_jobs, jobs.data(), sizeof(sttmfcc::FrameJob) * n_windows, cudaMemcpyHostToDevice, st));
-    sttmfcc::mfcc_jobs_kernel<<<n_windows, 256, 0, st>>>(e->tables, b->d_jobs);
+    sttmfcc::mfcc_jobs_kernel<<<(n_windows + sttmfcc::kWarpsPerBlock - 1) / sttmfcc::kWarpsPerBlock, sttmfcc::kWarpsPerBlock * 32, 0, st>>>(
+        e->tables, b->d_jobs, n_windows);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(st));  // `jobs` is a host temporary
     b->launches += 1;

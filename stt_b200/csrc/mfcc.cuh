@@ -1,4 +1,4 @@
-// K1: int16 PCM -> MFCC, one CTA per 32 ms analysis window.
+// K1: int16 PCM -> MFCC, one warp per 32 ms analysis window.
 //
 // Restates, per window, the reference chain (all double precision internally, like the TFLite kernels):
 //   stt.cc:105-128                    int16 -> f32 (x 1/32768), 512-sample window, hop 320, zero-padded tail
@@ -55,87 +55,107 @@ __device__ __forceinline__ int n_frames_for(int n, int win_len, int win_step) {
   return (n >= win_len ? (n - win_len) / win_step + 1 : 0) + 1;
 }
 
-__device__ __forceinline__ void mfcc_window(const MfccTables& tb, const int16_t* pcm, int n_valid, float* out_f32,
-                                            __half* out_f16) {
-  __shared__ double s_re[kFft];
-  __shared__ double s_im[kFft];
-  __shared__ float s_pow[kBins];
-  __shared__ double s_mel[kMaxChannels];
-  const int tid = threadIdx.x;  // 256 threads
-  for (int j = tid; j < kFft; j += blockDim.x) {
+constexpr int kWarpsPerBlock = 4;
+
+struct WarpScratch {
+  double re[kFft];
+  double im[kFft];
+  float pow[kBins + 3];
+  double mel[kMaxChannels];
+};
+
+// One WARP per analysis window (v1 used one 256-thread CTA per window and spent its time in __syncthreads; a warp
+// needs only __syncwarp between FFT stages and 20 windows are in flight per SM instead of 8).
+__device__ __forceinline__ void mfcc_window(const MfccTables& tb, WarpScratch& w, const int16_t* pcm, int n_valid,
+                                            float* out_f32, __half* out_f16) {
+  const int lane = threadIdx.x & 31;
+  for (int j = lane; j < kFft; j += 32) {
     double v = 0.0;
     if (j < tb.win_len && j < n_valid) v = (double)((float)pcm[j] * (1.0f / 32768.0f)) * tb.hann[j];
     const int r = __brev((unsigned)j) >> (32 - 9);
-    s_re[r] = v;
-    s_im[r] = 0.0;
+    w.re[r] = v;
+    w.im[r] = 0.0;
   }
-  __syncthreads();
+  __syncwarp();
 #pragma unroll 1
   for (int len = 2; len <= kFft; len <<= 1) {
     const int half = len >> 1;
-    for (int bf = tid; bf < kFft / 2; bf += blockDim.x) {
+    const int tstep = kFft / len;
+#pragma unroll 4
+    for (int bf = lane; bf < kFft / 2; bf += 32) {
       const int k = bf & (half - 1);
       const int i = ((bf - k) << 1) + k;
       const int j = i + half;
-      const int m = k * (kFft / len);
-      const double wr = tb.tw_re[m], wi = tb.tw_im[m];
-      const double xr = s_re[j] * wr - s_im[j] * wi, xi = s_re[j] * wi + s_im[j] * wr;
-      const double ur = s_re[i], ui = s_im[i];
-      s_re[j] = ur - xr;
-      s_im[j] = ui - xi;
-      s_re[i] = ur + xr;
-      s_im[i] = ui + xi;
+      const double wr = tb.tw_re[k * tstep], wi = tb.tw_im[k * tstep];
+      const double xr = w.re[j] * wr - w.im[j] * wi, xi = w.re[j] * wi + w.im[j] * wr;
+      const double ur = w.re[i], ui = w.im[i];
+      w.re[j] = ur - xr;
+      w.im[j] = ui - xi;
+      w.re[i] = ur + xr;
+      w.im[i] = ui + xi;
     }
-    __syncthreads();
+    __syncwarp();
   }
-  for (int i = tid; i < kBins; i += blockDim.x) s_pow[i] = (float)(s_re[i] * s_re[i] + s_im[i] * s_im[i]);
-  __syncthreads();
-  if (tid < tb.n_channels) {
+  for (int i = lane; i < kBins; i += 32) w.pow[i] = (float)(w.re[i] * w.re[i] + w.im[i] * w.im[i]);
+  __syncwarp();
+  for (int ch = lane; ch < tb.n_channels; ch += 32) {
     // same per-channel accumulation order as the reference's single pass over bins
     double acc = 0.0;
-    const int first = tb.chan_first_bin[tid], last = tb.chan_last_bin[tid];
+    const int first = tb.chan_first_bin[ch], last = tb.chan_last_bin[ch];
     if (first >= 0) {
       for (int i = first; i <= last; ++i) {
-        const double spec_val = sqrt((double)s_pow[i]);
+        const double spec_val = sqrt((double)w.pow[i]);
         const double weighted = spec_val * tb.weights[i];
-        const int ch = tb.band_mapper[i];
-        if (ch == tid) acc += weighted;
-        else if (ch + 1 == tid) acc += spec_val - weighted;
+        const int m = tb.band_mapper[i];
+        if (m == ch) acc += weighted;
+        else if (m + 1 == ch) acc += spec_val - weighted;
       }
     }
     if (acc < 1e-12) acc = 1e-12;
-    s_mel[tid] = log(acc);
+    w.mel[ch] = log(acc);
   }
-  __syncthreads();
-  if (tid < kFeatLanes) {
+  __syncwarp();
+  {
     float f = 0.f;
-    if (tid < tb.n_dct) {
+    if (lane < tb.n_dct) {
       double sum = 0.0;
-      for (int j = 0; j < tb.n_channels; ++j) sum += tb.cosines[tid * tb.n_channels + j] * s_mel[j];
+      for (int j = 0; j < tb.n_channels; ++j) sum += tb.cosines[lane * tb.n_channels + j] * w.mel[j];
       f = (float)sum;
-      if (out_f32) out_f32[tid] = f;
+      if (out_f32) out_f32[lane] = f;
     }
-    if (out_f16) out_f16[tid] = __float2half_rn(f);
+    if (out_f16) out_f16[lane] = __float2half_rn(f);  // kFeatLanes == 32: lanes >= n_dct store zeros
+  }
+  __syncwarp();
+}
+
+// grid-stride over (utterance, frame) pairs, one warp each
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_batch_kernel(const MfccTables tb, const BatchJob job, int n_utt) {
+  __shared__ WarpScratch scratch[kWarpsPerBlock];
+  WarpScratch& w = scratch[threadIdx.x >> 5];
+  const long long n_items = (long long)n_utt * job.frames_per_utt;
+  for (long long item = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); item < n_items;
+       item += (long long)gridDim.x * kWarpsPerBlock) {
+    const int b = (int)(item / job.frames_per_utt), f = (int)(item % job.frames_per_utt);
+    const int n = job.n_samples[b];
+    if (f >= n_frames_for(n, tb.win_len, tb.win_step)) continue;
+    const long long start = (long long)f * tb.win_step;
+    int n_valid = (int)(n - start);
+    if (n_valid > tb.win_len) n_valid = tb.win_len;
+    if (n_valid < 0) n_valid = 0;
+    mfcc_window(tb, w, job.pcm + b * job.stride + start, n_valid,
+                job.out_f32 ? job.out_f32 + ((size_t)b * job.frames_per_utt + f) * tb.n_dct : nullptr,
+                job.out_f16 ? job.out_f16 + ((size_t)b * job.f16_frames_per_utt + f + job.f16_row_offset) * kFeatLanes
+                            : nullptr);
   }
 }
 
-__global__ void __launch_bounds__(256) mfcc_batch_kernel(const MfccTables tb, const BatchJob job) {
-  const int b = blockIdx.x / job.frames_per_utt, f = blockIdx.x % job.frames_per_utt;
-  const int n = job.n_samples[b];
-  if (f >= n_frames_for(n, tb.win_len, tb.win_step)) return;
-  const long long start = (long long)f * tb.win_step;
-  int n_valid = (int)(n - start);
-  if (n_valid > tb.win_len) n_valid = tb.win_len;
-  if (n_valid < 0) n_valid = 0;
-  mfcc_window(tb, job.pcm + b * job.stride + start, n_valid,
-              job.out_f32 ? job.out_f32 + ((size_t)b * job.frames_per_utt + f) * tb.n_dct : nullptr,
-              job.out_f16 ? job.out_f16 + ((size_t)b * job.f16_frames_per_utt + f + job.f16_row_offset) * kFeatLanes
-                          : nullptr);
-}
-
-__global__ void __launch_bounds__(256) mfcc_jobs_kernel(const MfccTables tb, const FrameJob* jobs) {
-  const FrameJob j = jobs[blockIdx.x];
-  mfcc_window(tb, j.pcm, j.n_valid, j.out_f32, j.out_f16);
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_jobs_kernel(const MfccTables tb, const FrameJob* jobs, int n_jobs) {
+  __shared__ WarpScratch scratch[kWarpsPerBlock];
+  WarpScratch& w = scratch[threadIdx.x >> 5];
+  for (int item = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); item < n_jobs; item += gridDim.x * kWarpsPerBlock) {
+    const FrameJob j = jobs[item];
+    mfcc_window(tb, w, j.pcm, j.n_valid, j.out_f32, j.out_f16);
+  }
 }
 
 }  // namespace sttmfcc
