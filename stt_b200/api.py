@@ -55,7 +55,7 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile",
 ]
 
 
@@ -114,6 +114,8 @@ def lib():
     L.STTX_BatchFree.argtypes = [vp]
     L.STTX_BatchFree.restype = None
     L.STTX_BatchUpload.argtypes = [vp, POINTER(c_void_p), POINTER(c_uint), c_uint]
+    L.STTX_BatchHostBuffer.argtypes = [vp, c_uint]
+    L.STTX_BatchHostBuffer.restype = c_void_p
     L.STTX_BatchForward.argtypes = [vp]
     L.STTX_BatchDecode.argtypes = [vp, c_uint]
     L.STTX_BatchFetch.argtypes = [vp]
@@ -126,6 +128,7 @@ def lib():
     L.STTX_BatchKernelLaunches.restype = c_longlong
     L.STTX_BatchTimesteps.argtypes = [vp, c_uint]
     L.STTX_BatchPhaseCycles.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
+    L.STTX_BatchLstmProfile.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchLmStats.argtypes = [vp, POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchCopyFeatures.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchCopyProbs.argtypes = [vp, c_uint, c_void_p]
@@ -374,6 +377,11 @@ class Batch(object):
         self.n = n
         self._ok(lib().STTX_BatchUpload(self._impl, ptrs, lens, n), "BatchUpload")
 
+    def host_buffer(self, u, n_samples):
+        """numpy int16 view of utterance u's PINNED staging row; pass it to upload() for a copy-free H2D."""
+        ptr = lib().STTX_BatchHostBuffer(self._impl, u)
+        return np.ctypeslib.as_array(ctypes.cast(ptr, POINTER(c_short)), shape=(n_samples,))
+
     def forward(self):
         self._ok(lib().STTX_BatchForward(self._impl), "BatchForward")
 
@@ -406,6 +414,11 @@ class Batch(object):
         lib().STTX_BatchPhaseCycles(self._impl, arr)
         names = ("gate_cutoff", "child_discovery", "lm", "live_update", "children", "select", "commit", "unused")
         return dict(zip(names, [int(x) for x in arr]))
+
+    def lstm_profile(self):
+        arr = (ctypes.c_ulonglong * 3)()
+        lib().STTX_BatchLstmProfile(self._impl, arr)
+        return dict(zip(("grid_barrier_wait", "load_mma_span", "epilogue"), [int(x) for x in arr]))
 
     def lm_stats(self):
         w, c = ctypes.c_ulonglong(), ctypes.c_ulonglong()

@@ -518,6 +518,8 @@ void STTX_BatchFree(STTX_Batch* b) {
   delete b;
 }
 
+short* STTX_BatchHostBuffer(STTX_Batch* b, unsigned int u) { return stteng::batch_host_pcm(b->dev, (int)u); }
+
 int STTX_BatchUpload(STTX_Batch* b, const short* const* aBuffers, const unsigned int* aBufferSizes, unsigned int n) {
   return stteng::batch_upload(b->dev, aBuffers, aBufferSizes, (int)n) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
 }
@@ -555,6 +557,9 @@ int STTX_BatchGetTimings(STTX_Batch* b, STTX_Timings* out) {
 long long STTX_BatchKernelLaunches(STTX_Batch* b) { return stteng::batch_kernel_launches(b->dev); }
 int STTX_BatchPhaseCycles(STTX_Batch* b, unsigned long long* out8) {
   return stteng::batch_phase_cycles(b->dev, out8) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
+}
+int STTX_BatchLstmProfile(STTX_Batch* b, unsigned long long* out3) {
+  return stteng::batch_lstm_profile(b->dev, out3) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
 }
 int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls) {
   return stteng::batch_lm_stats(b->dev, words_scored, lm_calls) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;

@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
 // DecoderState::decode(num_results) (:278-326) + ModelState::decode_metadata's token/timestep extraction.
 struct FinalOut {
   int max_results, max_tokens;
-  int* n_results;        // [1]
+  int* n_results;        // [2]: number of results, overflow flag
   double* confidence;    // [max_results]
   int* n_tokens;         // [max_results]
   uint32_t* tokens;      // [max_results, max_tokens]
@@ -936,7 +936,10 @@ __global__ void __launch_bounds__(NT) decoder_finalize_kernel(Slot* slots, const
     }
     __syncthreads();
   }
-  if (tid == 0) *o.n_results = n_ret;
+  if (tid == 0) {
+    o.n_results[0] = n_ret;
+    o.n_results[1] = (int)s.scalars[6];  // decoder capacity overflow flag travels with the results
+  }
 }
 
 }  // namespace sttdec

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 
 #include "decoder.cuh"
 #include "gemm_tc.cuh"
@@ -417,6 +418,7 @@ struct Batch {
   __half* d_hall = nullptr;    // [(T_cap+1)*B_cap, Cp]
   float *d_c = nullptr, *d_h = nullptr;  // [B_cap, Cp]
   unsigned int* d_barrier = nullptr;
+  unsigned long long* d_lstm_prof = nullptr;  // [256 * 4]
   float* d_probs = nullptr;    // [B_cap, T_cap, n_classes]
   CUtensorMap tm_act_a, tm_act_b, tm_hall, tm_hall_out;
   __half* d_winmat = nullptr;  // fallback window matrix [T_cap*B_cap + 128, K1p]
@@ -558,6 +560,7 @@ Batch* batch_create(Engine* e, int B_cap, int max_samples, int beam_cap, int dec
   ok &= cudaMalloc((void**)&b->d_c, (size_t)B_cap * Cp * 4) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_h, (size_t)B_cap * Cp * 4) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_barrier, 64) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_lstm_prof, 8 * 4 * 1024) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_probs, (size_t)B_cap * b->T_cap * C * 4) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_win, (size_t)(b->T_cap + 1) * m.win_len * 2) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_jobs, sizeof(sttmfcc::FrameJob) * (b->T_cap + 1)) == cudaSuccess;
@@ -578,7 +581,7 @@ void batch_destroy(Batch* b) {
   if (!b) return;
   if (b->st) cudaStreamSynchronize(b->st);
   for (void* p : {(void*)b->d_pcm, (void*)b->d_nsamples, (void*)b->d_feat, (void*)b->d_feat32, (void*)b->d_act_a,
-                  (void*)b->d_act_b, (void*)b->d_xw, (void*)b->d_hall, (void*)b->d_c, (void*)b->d_h, (void*)b->d_barrier,
+                  (void*)b->d_act_b, (void*)b->d_xw, (void*)b->d_hall, (void*)b->d_c, (void*)b->d_h, (void*)b->d_barrier, (void*)b->d_lstm_prof,
                   (void*)b->d_probs, (void*)b->d_win, (void*)b->d_jobs, (void*)b->d_slot_mem, (void*)b->d_slots,
                   (void*)b->d_inputs, (void*)b->d_finals, (void*)b->d_out_mem, (void*)b->d_winmat})
     if (p) cudaFree(p);
@@ -592,17 +595,37 @@ void batch_destroy(Batch* b) {
   delete b;
 }
 
+int16_t* batch_host_pcm(Batch* b, int utt) {
+  return (utt >= 0 && utt < b->B_cap) ? b->h_pcm + (size_t)utt * b->S_cap : nullptr;
+}
+
 int batch_upload(Batch* b, const int16_t* const* pcm, const unsigned* n_samples, int B) {
   if (B < 1 || B > b->B_cap) return -1;
   const auto& m = b->e->hm;
   b->B = B;
   b->T_max = 0;
+  size_t to_copy = 0;
   for (int u = 0; u < B; ++u) {
     if ((int)n_samples[u] > b->S_cap) return -2;
     b->h_nsamples[u] = (int)n_samples[u];
-    memcpy(b->h_pcm + (size_t)u * b->S_cap, pcm[u], (size_t)n_samples[u] * 2);
     b->T[u] = frames_for((int)n_samples[u], m.win_len, m.win_step);
     b->T_max = std::max(b->T_max, b->T[u]);
+    if (pcm[u] != b->h_pcm + (size_t)u * b->S_cap) to_copy += (size_t)n_samples[u] * 2;
+  }
+  // stage into pinned memory (skipped for utterances the caller already wrote into batch_host_pcm(b, u))
+  auto stage = [&](int u0, int u1) {
+    for (int u = u0; u < u1; ++u) {
+      int16_t* dst = b->h_pcm + (size_t)u * b->S_cap;
+      if (pcm[u] != dst) memcpy(dst, pcm[u], (size_t)n_samples[u] * 2);
+    }
+  };
+  if (to_copy > (8u << 20) && B >= 8) {
+    const int nthr = 8;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthr; ++t) th.emplace_back(stage, B * t / nthr, B * (t + 1) / nthr);
+    for (auto& t : th) t.join();
+  } else {
+    stage(0, B);
   }
   cudaEventRecord(b->ev[0], b->st);
   // one strided copy when every utterance has the same length, else per utterance
@@ -755,6 +778,7 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
     sttlstm::LstmParams lp{};
     lp.B = B; lp.T = T; lp.n_cell = Cp; lp.xw = b->d_xw; lp.h_all = b->d_hall; lp.c_state = b->d_c; lp.h_state = b->d_h;
     lp.barrier = b->d_barrier;
+    lp.prof = b->d_lstm_prof;
     const int grid = Cp / sttlstm::kCellsPerCta;
     if (launch_lstm(b, lp, grid, B, st)) return -1;
   }
@@ -956,11 +980,9 @@ int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out) {
   cudaEventRecord(b->ev[11], st);
   CUDA_OK(cudaStreamSynchronize(st));
   cudaEventElapsedTime(&b->times.d2h, b->ev[10], b->ev[11]);
-  // overflow check: a decoder that ran out of arena space must fail loudly
+  // overflow check: a decoder that ran out of arena space must fail loudly (flag written by the finalize kernel)
   for (int u = 0; u < b->B; ++u) {
-    uint32_t sc[8];
-    CUDA_OK(cudaMemcpy(sc, b->h_slots[u].scalars, sizeof(sc), cudaMemcpyDeviceToHost));
-    if (sc[6]) {
+    if (reinterpret_cast<const int*>(b->h_out_mem + b->out_bytes_per_utt * u)[1]) {
       fprintf(stderr, "[stt_b200] decoder capacity exceeded for utterance %d\n", u);
       return -3;
     }
@@ -977,6 +999,16 @@ int batch_phase_cycles(Batch* b, unsigned long long* out8) {
     CUDA_OK(cudaMemcpy(ph, b->h_slots[u].phase_cycles, sizeof(ph), cudaMemcpyDeviceToHost));
     for (int q = 0; q < 8; ++q) out8[q] += ph[q];
   }
+  return 0;
+}
+
+int batch_lstm_profile(Batch* b, unsigned long long* out3) {
+  const int grid = b->e->Cp / sttlstm::kCellsPerCta;
+  std::vector<unsigned long long> h((size_t)grid * 4);
+  CUDA_OK(cudaMemcpy(h.data(), b->d_lstm_prof, h.size() * 8, cudaMemcpyDeviceToHost));
+  out3[0] = out3[1] = out3[2] = 0;
+  for (int g = 0; g < grid; ++g)
+    for (int k = 0; k < 3; ++k) out3[k] = std::max(out3[k], h[(size_t)g * 4 + k]);
   return 0;
 }
 

@@ -39,6 +39,7 @@ int engine_num_sms(const Engine* e);
 Batch* batch_create(Engine* e, int B_cap, int max_samples, int beam_cap, int dec_T_cap, std::string* err);
 void batch_destroy(Batch* b);
 // Offline use: upload -> forward -> decode -> fetch.
+int16_t* batch_host_pcm(Batch* b, int utt);                // pinned staging row (capacity max_samples) for zero-copy upload
 int batch_upload(Batch* b, const int16_t* const* pcm, const unsigned* n_samples, int B);
 int batch_forward(Batch* b);                                 // MFCC + acoustic model -> probs in HBM
 int batch_decode(Batch* b, int beam, int num_results);       // resets the decoder, runs all timesteps, finalises
@@ -47,6 +48,7 @@ const StageTimes& batch_times(const Batch* b);
 long long batch_kernel_launches(const Batch* b);
 // Debug / test access
 int batch_phase_cycles(Batch* b, unsigned long long* out8);  // instrumentation: summed over utterances
+int batch_lstm_profile(Batch* b, unsigned long long* out3);  // max over CTAs: barrier-wait, load+MMA span, epilogue cycles
 int batch_lm_stats(Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls);  // instrumentation
 int batch_T(const Batch* b, int utt);                        // timesteps of utterance `utt` after upload
 int batch_copy_features(Batch* b, int utt, float* out);      // [T, n_input] fp32 MFCC

@@ -44,6 +44,7 @@ struct LstmParams {
   float* c_state;        // [B, n_cell] fp32 in/out
   float* h_state;        // [B, n_cell] fp32 out (final h, full precision)
   unsigned int* barrier; // zero-initialised counter
+  unsigned long long* prof; // [gridDim.x * 4] instrumentation (cycles): grid-barrier wait, load+MMA span, epilogue, -
 };
 
 template <int MT, int STAGES>
@@ -109,6 +110,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const int pre = num_k_blocks < STAGES ? num_k_blocks : STAGES;
+      unsigned long long prof_wait = 0;
       for (int t = 0; t < p.T; ++t) {
         // weight tiles of the first `pre` k-blocks: independent of h, requested before the grid barrier
         int st2 = stage;
@@ -120,12 +122,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           if (++st2 == STAGES) { st2 = 0; ph2 ^= 1; }
         }
         if (t > 0) {
+          const long long w0 = clock64();
           const unsigned int target = (unsigned int)t * gridDim.x;
           unsigned int seen;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.barrier) : "memory");
           } while (seen < target);
           ptx::fence_proxy_async();  // other CTAs' generic-proxy stores of h_{t-1} -> async-proxy (TMA) reads
+          prof_wait += (unsigned long long)(clock64() - w0);
         }
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -144,15 +148,19 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.prof) p.prof[blockIdx.x * 4 + 0] = prof_wait;
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = ptx::make_idesc_f16(BLOCK_M, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
+    unsigned long long prof_mma = 0;
+    long long m0 = 0;
     for (int t = 0; t < p.T; ++t) {
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
+        if (kb == 0) m0 = clock64();
         ptx::tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
@@ -172,7 +180,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      prof_mma += (unsigned long long)(clock64() - m0);
     }
+    if (lane == 0 && p.prof) p.prof[blockIdx.x * 4 + 1] = prof_mma;
   } else {
     // ===================== epilogue warps: gates -> (c, h) =====================
     const int ew = warp_idx - 2;              // 0..7
@@ -189,6 +199,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
     }
     const size_t xw_row = (size_t)4 * p.n_cell;
     const int ncol0 = n0 + chalf * 32;
+    unsigned long long prof_epi = 0;
     for (int t = 0; t < p.T; ++t) {
       // this step's xw values are loaded while the MMAs run; next step's rows are pulled towards L2
       float4 xv[MT][8];
@@ -203,6 +214,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           asm volatile("prefetch.global.L2 [%0];" ::"l"(p.xw + ((size_t)(t + 1) * p.B + b) * xw_row + ncol0));
       }
       ptx::mbar_wait(tmem_full_bar, t & 1);
+      const long long e0 = clock64();
       ptx::tc_fence_after();
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
@@ -247,8 +259,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
         __threadfence();
         ptx::fence_proxy_async();
         atomicAdd(p.barrier, 1u);
+        prof_epi += (unsigned long long)(clock64() - e0);
       }
     }
+    if (threadIdx.x == 64 && p.prof) p.prof[blockIdx.x * 4 + 2] = prof_epi;
   }
 
   ptx::tc_fence_before();
