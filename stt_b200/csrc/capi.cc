@@ -277,10 +277,6 @@ Metadata* stream_decode_metadata(const StreamingState* s, unsigned int num_resul
 
 int create_stream_impl(ModelState* ms, StreamingState** retval, bool keep_emissions) {
   *retval = nullptr;
-  if (!ms->hot_words_.empty() && !ms->warned_hot_words) {
-    fprintf(stderr, "[stt_b200] warning: hot-word boosts are recorded but not applied by the GPU decoder yet\n");
-    ms->warned_hot_words = true;
-  }
   std::unique_ptr<StreamingState> ctx(new StreamingState());
   ctx->model_ = ms;
   ctx->keep_emissions_ = keep_emissions;
@@ -298,6 +294,12 @@ int create_stream_impl(ModelState* ms, StreamingState** retval, bool keep_emissi
       if (ctx->dev) stteng::batch_destroy(ctx->dev);
       return STT_ERR_FAIL_CREATE_STREAM;
     }
+  }
+  {  // hot words are snapshotted per stream (stt.cc:542-547)
+    std::vector<std::string> w;
+    std::vector<float> bo;
+    for (const auto& kv : ms->hot_words_) { w.push_back(kv.first); bo.push_back(kv.second); }
+    stteng::batch_set_hot_words(ctx->dev, w, bo);
   }
   ctx->audio_buffer_.reserve(stteng::engine_model(ms->engine).win_len);
   *retval = ctx.release();
@@ -527,6 +529,12 @@ int STTX_BatchForward(STTX_Batch* b) { return stteng::batch_forward(b->dev) ? ST
 int STTX_BatchDecode(STTX_Batch* b, unsigned int aNumResults) {
   const unsigned int beam = std::max(1u, b->model->beam_width_);
   if (beam > b->beam_cap) return STT_ERR_INVALID_SHAPE;
+  {
+    std::vector<std::string> w;
+    std::vector<float> bo;
+    for (const auto& kv : b->model->hot_words_) { w.push_back(kv.first); bo.push_back(kv.second); }
+    stteng::batch_set_hot_words(b->dev, w, bo);
+  }
   return stteng::batch_decode(b->dev, (int)beam, (int)std::max(1u, aNumResults)) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
 }
 int STTX_BatchFetch(STTX_Batch* b) { return stteng::batch_fetch(b->dev, &b->results) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK; }

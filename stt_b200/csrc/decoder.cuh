@@ -41,6 +41,7 @@ constexpr float kFltMin = 1.175494351e-38f;   // NUM_FLT_MIN
 constexpr int kMaxClasses = 64;
 constexpr int kMaxWordBytes = 128;
 constexpr int kStateWords = sttscorer::kMaxOrder - 1;
+constexpr int kMaxHotWords = 32;
 
 struct Node {            // one surviving prefix (PathTrie node), 32 bytes
   uint32_t parent;       // arena id, kNone for the root
@@ -101,6 +102,10 @@ struct DecodeParams {
   // that have an arc}, per arc {ilabel, dictionary state of the child = Start() if the arc's target is final}
   const uint2* fst_state2;
   const int2* fst_arc2;
+  // hot words (ctc_beam_search_decoder.cpp:224-236): vocabulary ids and boosts, snapshotted when the stream starts
+  int n_hot;
+  uint32_t hot_id[kMaxHotWords];
+  float hot_boost[kMaxHotWords];
 };
 
 struct StepInput {
@@ -299,6 +304,36 @@ __device__ double lm_eval_node(const Slot& s, const sttscorer::ScorerView& v, ui
   const uint32_t nw = meta >> 16;
   *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
   return cond;
+}
+
+// Hot-word boost of one LM call: every word of the <=order-word window that is a hot word adds its boost
+// (ctc_beam_search_decoder.cpp:224-236; the window is make_ngram's, walked through the cached word ids).
+__device__ float hot_word_boost(const Slot& s, const DecodeParams& p, uint32_t node, uint32_t first_wid) {
+  float per_word[sttscorer::kMaxOrder];
+  int n = 0;
+  const int order = (int)p.scorer.order;
+  uint32_t wid = first_wid;  // id of the word ending at `cur`
+  uint32_t cur = node;
+  while (n < order) {
+    const Node nd = s.nodes[cur];
+    if (nd.chr == kRootChar) break;
+    float b = 0.0f;
+    bool hit = false;
+    if (wid != 0)
+      for (int h = 0; h < p.n_hot; ++h)
+        if (p.hot_id[h] == wid) { b = p.hot_boost[h]; hit = true; }
+    per_word[n++] = hit ? b : 0.0f;
+    const uint32_t stop = nd.last_space;  // the space before this word
+    if (stop == kNone) break;
+    const Node sp = s.nodes[stop];
+    wid = sp.word_id;   // a space node carries the id of the word it terminates = the previous word of the window
+    cur = sp.parent;    // ... which ends at the space's parent
+  }
+  // the reference adds the boosts in n-gram order, oldest word first (float accumulation)
+  float boost = 0.0f;
+  for (int i = n - 1; i >= 0; --i)
+    if (per_word[i] != 0.0f) boost += per_word[i];
+  return boost;
 }
 
 // ------------------------------------------------------------------------------------------------ init
@@ -523,7 +558,9 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           const uint32_t i = sm.lmq[q];
           uint32_t wid, nw;
           // (float)(cond * alpha): ctc_beam_search_decoder.cpp:239 (hot-word boost = 0)
-          sm.lmterm[i] = (float)(lm_eval_node(s, sv, L.node[i], &wid, &nw) * sv.alpha);
+          double cond = lm_eval_node(s, sv, L.node[i], &wid, &nw);
+          if (p.n_hot > 0) cond += (double)hot_word_boost(s, p, L.node[i], wid);
+          sm.lmterm[i] = (float)(cond * sv.alpha);
           sm.lmwid[i] = wid;
           atomicAdd(&s_u[6], nw);
           atomicAdd(&s_u[7], 1u);

@@ -434,6 +434,8 @@ struct Batch {
   uint8_t* h_out_mem = nullptr;  // pinned mirror
   size_t out_bytes_per_utt = 0;
   int cur_beam = 0, cur_results = 1;
+  std::vector<uint32_t> hot_ids;   // hot words of the current decode / stream (vocabulary ids)
+  std::vector<float> hot_boosts;
   // streaming
   int stream_frames = 0;  // frames currently in d_feat (utterance 0)
   int16_t* d_win = nullptr;
@@ -846,6 +848,11 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
   if (e->has_scorer) dp.scorer = e->scorer_view;
   dp.fst_state2 = e->fst_state2;
   dp.fst_arc2 = e->fst_arc2;
+  dp.n_hot = e->has_scorer ? (int)std::min<size_t>(b->hot_ids.size(), sttdec::kMaxHotWords) : 0;
+  for (int h = 0; h < dp.n_hot; ++h) {
+    dp.hot_id[h] = b->hot_ids[h];
+    dp.hot_boost[h] = b->hot_boosts[h];
+  }
   return dp;
 }
 
@@ -950,6 +957,32 @@ void parse_results(const Batch* b, const uint8_t* base, std::vector<Decoded>* ou
 }
 
 }  // namespace
+
+int batch_set_hot_words(Batch* b, const std::vector<std::string>& words, const std::vector<float>& boosts) {
+  // Words outside the LM vocabulary can never equal a word of a scored n-gram (every scored word passed the
+  // dictionary, whose words come from the LM vocabulary), so they are dropped here.
+  b->hot_ids.clear();
+  b->hot_boosts.clear();
+  const Engine* e = b->e;
+  if (!e->has_scorer) return 0;
+  std::vector<uint8_t> host;  // the vocabulary hashes live at the start of the blob; read them back once
+  const sttscorer::ScorerView& dv = e->scorer_view;
+  host.resize(dv.vocab_off + dv.vocab_count * 8 + 16);
+  CUDA_OK(cudaMemcpy(host.data(), e->scorer_blob, host.size(), cudaMemcpyDeviceToHost));
+  sttscorer::ScorerView hv = dv;
+  hv.blob = host.data();
+  for (size_t i = 0; i < words.size(); ++i) {
+    const uint32_t id = sttscorer::vocab_index(hv, reinterpret_cast<const uint8_t*>(words[i].data()), (uint32_t)words[i].size());
+    if (id != 0) {
+      b->hot_ids.push_back(id);
+      b->hot_boosts.push_back(boosts[i]);
+    }
+  }
+  if (b->hot_ids.size() > (size_t)sttdec::kMaxHotWords) {
+    fprintf(stderr, "[stt_b200] more than %d in-vocabulary hot words: the rest are ignored\n", sttdec::kMaxHotWords);
+  }
+  return 0;
+}
 
 int batch_decode(Batch* b, int beam, int num_results) {
   if (b->B < 1 || beam < 1 || beam > b->beam_cap) return -1;

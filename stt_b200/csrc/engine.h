@@ -42,6 +42,7 @@ void batch_destroy(Batch* b);
 int16_t* batch_host_pcm(Batch* b, int utt);                // pinned staging row (capacity max_samples) for zero-copy upload
 int batch_upload(Batch* b, const int16_t* const* pcm, const unsigned* n_samples, int B);
 int batch_forward(Batch* b);                                 // MFCC + acoustic model -> probs in HBM
+int batch_set_hot_words(Batch* b, const std::vector<std::string>& words, const std::vector<float>& boosts);
 int batch_decode(Batch* b, int beam, int num_results);       // resets the decoder, runs all timesteps, finalises
 int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out);
 const StageTimes& batch_times(const Batch* b);

@@ -61,6 +61,14 @@ __device__ __forceinline__ float tanh_fast(float x) {
   // 1 - 2/(1+e^{2x}); saturates cleanly for |x| large (e^{2x} -> inf gives 1, -> 0 gives -1)
   return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
 }
+// One MUFU op (rel. error ~2^-11): used only on the h = sigmoid(o) * tanh(c) path, whose result is rounded to fp16
+// (2^-11) anyway; the cell-state update keeps the more accurate ex2/rcp forms so errors do not accumulate in c.
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
 
 // tmap_h: box = {64, 128 / CS} rows of h_all; tmap_wh: box = {64, 64} rows of Wh.
 template <int MT, int STAGES, int CS>
@@ -232,7 +240,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           const float go = __uint_as_float(r[q * 4 + 3]) + xv[mt][q].w;
           const float cn = sigmoid_fast(gf) * c_reg[mt][q] + sigmoid_fast(gi) * tanh_fast(gj);
           c_reg[mt][q] = cn;
-          h_last[q] = sigmoid_fast(go) * tanh_fast(cn);
+          h_last[q] = sigmoid_mufu(go) * tanh_mufu(cn);
         }
         if (valid) {
           uint32_t hpk[4];

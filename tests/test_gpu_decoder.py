@@ -114,6 +114,49 @@ def test_decoder_alpha_beta_sweep(ref_decoder, small_model, vocab_words, english
             _compare(b.results(0), o.ref_decode(probs[0], alpha, 100, sc), "alpha=%g beta=%g" % (a, be))
 
 
+def test_decoder_hot_words_match_reference(ref_decoder, small_model, vocab_words, english):
+    """ctc_beam_search_decoder.cpp:224-239: every window word that is a hot word adds its boost before the alpha scale."""
+    import ctypes
+    from stt_b200 import synth
+    o = ref_decoder
+    R = o.ref()
+    alpha = o.RefAlphabet(english)
+    sc = o.RefScorer(SCORER, alpha)
+    beam, T = 100, 150
+    hot = {"the": 7.5, "and": -4.0, "of": 3.25, "notaword": 9.0, vocab_words[10]: 6.0, vocab_words[200]: -2.5}
+    m = _model(small_model, beam)
+    for w, b in hot.items():
+        m.addHotWord(w, b)
+    for u in range(4):
+        probs = synth.make_ctc_probs(vocab_words, T, utt=5150 + u)
+        bt = m.createBatch(1, T * 320)
+        bt.set_probs(probs[None], [T])
+        bt.decode(num_results=2)
+        bt.fetch()
+        words = b"".join(w.encode() + b"\0" for w in hot)
+        boosts = np.array(list(hot.values()), np.float32)
+        d = R.ref_decoder_new(alpha.h, beam, 1.0, 40, sc.h, words, boosts.ctypes.data, len(hot))
+        p64 = np.ascontiguousarray(probs, np.float64)
+        R.ref_decoder_next(d, p64.ctypes.data, T, 29)
+        conf = np.zeros(2, np.float64); nt = np.zeros(2, np.int32)
+        tok = np.zeros((2, T), np.uint32); ts = np.zeros((2, T), np.uint32)
+        n = R.ref_decoder_decode(d, 2, T, conf.ctypes.data, nt.ctypes.data, tok.ctypes.data, ts.ctypes.data)
+        R.ref_decoder_free(d)
+        ref = [(conf[r], tok[r, :nt[r]], ts[r, :nt[r]]) for r in range(n)]
+        _compare(bt.results(0), ref, "hot words utt=%d" % u)
+    # and a hot word that occurs in the transcript must change its confidence
+    m2 = _model(small_model, beam)
+    probs = synth.make_ctc_probs(vocab_words, T, utt=5150)
+    b2 = m2.createBatch(1, T * 320)
+    b2.set_probs(probs[None], [T]); b2.decode(1); b2.fetch()
+    base_conf, base_tok, _ = b2.results(0)[0]
+    first_word = alpha.decode(base_tok).split()[0]
+    m2.addHotWord(first_word, 3.0)
+    b3 = m2.createBatch(1, T * 320)
+    b3.set_probs(probs[None], [T]); b3.decode(1); b3.fetch()
+    assert b3.results(0)[0][0] > base_conf
+
+
 def test_decoder_against_committed_golden(small_model):
     """Golden vectors produced by the reference decoder in the build container (tests/golden/make_golden.py)."""
     g = np.load(os.path.join(GOLDEN, "decoder_golden.npz"), allow_pickle=True)
