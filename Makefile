@@ -13,7 +13,11 @@ BUILD     := build
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/stt_capi.h
 
 .PHONY: all oracle clean
-all: $(OUT)
+CLI       := stt_b200/stt
+all: $(OUT) $(CLI)
+
+$(CLI): $(SRC)/client.cc include/stt_capi.h $(OUT)
+	$(CXX) -O2 -std=c++17 -o $@ $(SRC)/client.cc -Lstt_b200 -lstt_b200 -Wl,-rpath,'$$ORIGIN' -L$(CUDA_HOME)/lib64 -Wl,-rpath,$(CUDA_HOME)/lib64
 
 $(BUILD)/engine.o: $(SRC)/engine.cu $(HDRS)
 	@mkdir -p $(BUILD)
@@ -31,4 +35,4 @@ oracle:
 	if [ -d /root/reference ]; then $(MAKE) -C oracle -j8 ref; fi
 
 clean:
-	rm -rf $(BUILD) $(OUT)
+	rm -rf $(BUILD) $(OUT) $(CLI)

@@ -183,6 +183,8 @@ STT_EXPORT int STTX_BatchTimesteps(STTX_Batch* b, unsigned int u);
 STT_EXPORT int STTX_BatchCopyFeatures(STTX_Batch* b, unsigned int u, float* out);  /* [T, n_input] */
 STT_EXPORT int STTX_BatchCopyProbs(STTX_Batch* b, unsigned int u, float* out);     /* [T, n_classes] */
 STT_EXPORT int STTX_BatchSetProbs(STTX_Batch* b, const float* probs, const int* T, unsigned int n, unsigned int T_stride);
+/* decoder-only entry (the reference's Python ctc_beam_search_decoder_batch takes f64 probabilities) */
+STT_EXPORT int STTX_BatchSetProbs64(STTX_Batch* b, const double* probs, const int* T, unsigned int n, unsigned int T_stride);
 STT_EXPORT int STTX_DebugGemm(int M, int N, int K, const unsigned short* a_f16, const unsigned short* w_f16,
                               const float* bias, int epilogue, float relu_clip, void* out, float* ms);
 STT_EXPORT int STTX_ModelInfo(const ModelState* aCtx, unsigned int* n_classes, unsigned int* n_input, unsigned int* n_hidden,

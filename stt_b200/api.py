@@ -55,7 +55,7 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64",
 ]
 
 
@@ -133,6 +133,7 @@ def lib():
     L.STTX_BatchCopyFeatures.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchCopyProbs.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchSetProbs.argtypes = [vp, c_void_p, c_void_p, c_uint, c_uint]
+    L.STTX_BatchSetProbs64.argtypes = [vp, c_void_p, c_void_p, c_uint, c_uint]
     L.STTX_DebugGemm.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                  POINTER(c_float)]
     L.STTX_ModelInfo.argtypes = [vp] + [POINTER(c_uint)] * 5
@@ -444,6 +445,14 @@ class Batch(object):
         out = np.zeros((T, info["n_classes"]), np.float32)
         lib().STTX_BatchCopyProbs(self._impl, u, out.ctypes.data)
         return out
+
+    def set_probs64(self, probs, lengths):
+        """probs: float64 [B, T_stride, C] (the Python decoder API's input type)."""
+        p = np.ascontiguousarray(probs, dtype=np.float64)
+        t = np.ascontiguousarray(lengths, dtype=np.int32)
+        self.n = p.shape[0]
+        self._ok(lib().STTX_BatchSetProbs64(self._impl, p.ctypes.data, t.ctypes.data, p.shape[0], p.shape[1]),
+                 "BatchSetProbs64")
 
     def set_probs(self, probs, lengths):
         """probs: float32 [B, T_stride, C]; lengths: per-utterance T.  Decoder-only parity tests."""

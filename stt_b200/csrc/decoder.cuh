@@ -109,7 +109,9 @@ struct DecodeParams {
 };
 
 struct StepInput {
-  const float* probs;    // [T, n_classes] f32 softmax rows for this slot
+  const float* probs;     // [T, n_classes] f32 softmax rows for this slot (the C API path: stt.cc:327 widens f32 to f64)
+  const double* probs64;  // or f64 rows as the Python decoder API passes them (swigwrapper.i:39-41); the class
+                          // log-prob uses (float)p (:333), the gate and min_cutoff use the double (:125,:143)
   int n_steps;
 };
 
@@ -466,13 +468,20 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     L.pos[i] = st.x;
     L.mask[i] = st.y;
   }
+  const bool use64 = in.probs64 != nullptr;
+  auto prob_f = [&](int row, int c) -> float {
+    return use64 ? (float)in.probs64[(size_t)row * C + c] : in.probs[(size_t)row * C + c];
+  };
+  auto prob_d = [&](int row, int c) -> double {
+    return use64 ? in.probs64[(size_t)row * C + c] : (double)in.probs[(size_t)row * C + c];
+  };
   for (uint32_t i = tid; i < (uint32_t)WC; i += NT) sm.child[i] = 0;
   if (in.n_steps > 0) {
     // class log-probs of the first row (get_pruned_emissions :328-358 with the C-API's cutoff_prob = 1.0,
     // cutoff_top_n = 40 >= n_classes: no pruning, index order, blank last); later rows are prepared one step ahead
-    if (tid < C) s_logp2[0][tid] = sttmath::glibc_logf(in.probs[tid] + kFltMin);
+    if (tid < C) s_logp2[0][tid] = sttmath::glibc_logf(prob_f(0, tid) + kFltMin);
     if (tid == 0) {
-      const double pb = (double)in.probs[blank];
+      const double pb = prob_d(0, blank);
       s_gate[0] = pb < 0.999 ? 1u : 0u;
       s_logblank[0] = log(pb);
     }
@@ -482,7 +491,6 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
 #define PHASE_MARK(k) do { if (tid == 0) { const long long _t = clock64(); s_ph[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
 
   for (int step = 0; step < in.n_steps; ++step, ++abs_t) {
-    const float* prob = in.probs + (size_t)step * C;
     LiveList<WC>& L = sm.live[cur];
     LiveList<WC>& Nx = sm.live[cur ^ 1];
     // ---- phase 0: gate (:125-132), the beam's minimum score, and which (parent, label) pairs already have a live
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     const float* s_logp = s_logp2[cb];
     float next_p = 0.f;
     const bool have_next = (step + 1 < in.n_steps);
-    if (have_next && tid < C) next_p = prob[C + tid];
+    if (have_next && tid < C) next_p = prob_f(step + 1, tid);
     if (start_expanding | s_gate[cb]) {
       for (uint32_t j = tid; j < n_live; j += NT) {
         const uint32_t pn = L.pnode[j];
@@ -518,7 +526,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       if (have_next) {
         if (tid < C) s_logp2[cb ^ 1][tid] = sttmath::glibc_logf(next_p + kFltMin);
         if (tid == 0) {
-          const double pb = (double)prob[C + blank];
+          const double pb = prob_d(step + 1, blank);
           s_gate[cb ^ 1] = pb < 0.999 ? 1u : 0u;
           s_logblank[cb ^ 1] = log(pb);
         }
@@ -707,7 +715,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     if (have_next) {
       if (tid < C) s_logp2[cb ^ 1][tid] = sttmath::glibc_logf(next_p + kFltMin);
       if (tid == NT - 1) {
-        const double pb = (double)prob[C + blank];
+        const double pb = prob_d(step + 1, blank);
         s_gate[cb ^ 1] = pb < 0.999 ? 1u : 0u;
         s_logblank[cb ^ 1] = log(pb);
       }

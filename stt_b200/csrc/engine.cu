@@ -420,6 +420,8 @@ struct Batch {
   unsigned int* d_barrier = nullptr;
   unsigned long long* d_lstm_prof = nullptr;  // [256 * 4]
   float* d_probs = nullptr;    // [B_cap, T_cap, n_classes]
+  double* d_probs64 = nullptr; // optional f64 copy set by batch_set_probs64 (Python decoder API)
+  bool use_probs64 = false;
   CUtensorMap tm_act_a, tm_act_b, tm_hall, tm_hall_out;
   __half* d_winmat = nullptr;  // fallback window matrix [T_cap*B_cap + 128, K1p]
   CUtensorMap tm_winmat;
@@ -583,7 +585,7 @@ void batch_destroy(Batch* b) {
   if (!b) return;
   if (b->st) cudaStreamSynchronize(b->st);
   for (void* p : {(void*)b->d_pcm, (void*)b->d_nsamples, (void*)b->d_feat, (void*)b->d_feat32, (void*)b->d_act_a,
-                  (void*)b->d_act_b, (void*)b->d_xw, (void*)b->d_hall, (void*)b->d_c, (void*)b->d_h, (void*)b->d_barrier, (void*)b->d_lstm_prof,
+                  (void*)b->d_act_b, (void*)b->d_xw, (void*)b->d_hall, (void*)b->d_c, (void*)b->d_h, (void*)b->d_barrier, (void*)b->d_lstm_prof, (void*)b->d_probs64,
                   (void*)b->d_probs, (void*)b->d_win, (void*)b->d_jobs, (void*)b->d_slot_mem, (void*)b->d_slots,
                   (void*)b->d_inputs, (void*)b->d_finals, (void*)b->d_out_mem, (void*)b->d_winmat})
     if (p) cudaFree(p);
@@ -802,6 +804,7 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
 
 int batch_forward(Batch* b) {
   Engine* e = b->e;
+  b->use_probs64 = false;
   const auto& m = e->hm;
   if (b->B < 1) return -1;
   cudaStream_t st = b->st;
@@ -995,6 +998,7 @@ int batch_decode(Batch* b, int beam, int num_results) {
   std::vector<sttdec::StepInput> in(b->B);
   for (int u = 0; u < b->B; ++u) {
     in[u].probs = b->d_probs + (size_t)u * b->T_cap * b->e->hm.n_classes;
+    in[u].probs64 = b->use_probs64 ? b->d_probs64 + (size_t)u * b->T_cap * b->e->hm.n_classes : nullptr;
     in[u].n_steps = b->T[u];
   }
   if (decoder_steps(b, b->B, in, beam)) return -1;
@@ -1069,8 +1073,26 @@ int batch_copy_probs(Batch* b, int utt, float* out) {
   CUDA_OK(cudaMemcpy(out, b->d_probs + (size_t)utt * b->T_cap * C, (size_t)b->T[utt] * C * 4, cudaMemcpyDeviceToHost));
   return b->T[utt];
 }
+int batch_set_probs64(Batch* b, const double* probs, const int* T, int B, int T_stride) {
+  if (B < 1 || B > b->B_cap) return -1;
+  const int C = b->e->hm.n_classes;
+  if (!b->d_probs64) CUDA_OK(cudaMalloc((void**)&b->d_probs64, (size_t)b->B_cap * b->T_cap * C * 8));
+  b->B = B;
+  b->T_max = 0;
+  for (int u = 0; u < B; ++u) {
+    if (T[u] > b->T_cap) return -2;
+    b->T[u] = T[u];
+    b->T_max = std::max(b->T_max, T[u]);
+    CUDA_OK(cudaMemcpy(b->d_probs64 + (size_t)u * b->T_cap * C, probs + (size_t)u * T_stride * C, (size_t)T[u] * C * 8,
+                       cudaMemcpyHostToDevice));
+  }
+  b->use_probs64 = true;
+  return 0;
+}
+
 int batch_set_probs(Batch* b, const float* probs, const int* T, int B, int T_stride) {
   if (B < 1 || B > b->B_cap) return -1;
+  b->use_probs64 = false;
   const int C = b->e->hm.n_classes;
   b->B = B;
   b->T_max = 0;
@@ -1146,6 +1168,7 @@ int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_p
   // DecoderState::next on the new rows
   std::vector<sttdec::StepInput> in(1);
   in[0].probs = b->d_probs;
+  in[0].probs64 = nullptr;
   in[0].n_steps = n_timesteps;
   if (decoder_steps(b, 1, in, b->cur_beam)) return -1;
   b->last_run_T = n_timesteps;

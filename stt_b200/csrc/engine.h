@@ -54,7 +54,8 @@ int batch_lm_stats(Batch* b, unsigned long long* words_scored, unsigned long lon
 int batch_T(const Batch* b, int utt);                        // timesteps of utterance `utt` after upload
 int batch_copy_features(Batch* b, int utt, float* out);      // [T, n_input] fp32 MFCC
 int batch_copy_probs(Batch* b, int utt, float* out);         // [T, n_classes]
-int batch_set_probs(Batch* b, const float* probs, const int* T, int B, int T_stride);  // decoder-only tests
+int batch_set_probs(Batch* b, const float* probs, const int* T, int B, int T_stride);  // decoder-only use
+int batch_set_probs64(Batch* b, const double* probs, const int* T, int B, int T_stride);
 // Streaming use (B == 1): the caller owns framing (stt.cc buffer logic) and feeds analysis windows.
 int batch_stream_reset(Batch* b, int beam);                                 // zero LSTM state, DecoderState::init
 int batch_stream_push_windows(Batch* b, const int16_t* windows, const int* n_valid, int n_windows, int n_zero_frames);
