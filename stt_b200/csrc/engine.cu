@@ -14,6 +14,7 @@
 
 #include "decoder.cuh"
 #include "gemm_tc.cuh"
+#include "lstm2_tc.cuh"
 #include "lstm_tc.cuh"
 #include "mfcc.cuh"
 #include "scorer_image.h"
@@ -720,8 +721,47 @@ int launch_lstm_mt(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream
   return launch_lstm_inst<MT, STAGES, 1>(b, lp, grid, st, false, &unused);
 }
 
+// CTA-pair (cta_group::2) kernel for 129..256 utterances; returns 1 if it cannot be used.
+int launch_lstm_pair(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st) {
+  static int usable = -1;  // -1 unknown, 0 no, 1 yes
+  static const char* env = getenv("STT_B200_LSTM_PAIR");
+  if (env && atoi(env) == 0) return 1;
+  if (grid % 2 != 0) return 1;
+  using L = sttlstm::PairSmem;
+  auto kern = sttlstm::lstm_pair_kernel;
+  cudaLaunchConfig_t cfgl{};
+  cfgl.gridDim = dim3(grid);
+  cfgl.blockDim = dim3(sttlstm::kNumThreads);
+  cfgl.dynamicSmemBytes = L::kTotal;
+  cfgl.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = 2;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfgl.attrs = attrs;
+  cfgl.numAttrs = 2;
+  if (usable < 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) { cudaGetLastError(); usable = 0; return 1; }
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfgl) != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
+    usable = (n_clusters * 2 >= grid) ? 1 : 0;
+    if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] LSTM pair kernel: %d co-resident pairs, usable=%d\n", n_clusters, usable);
+  }
+  if (!usable) return 1;
+  CUtensorMap tm_h;
+  const size_t rows = (size_t)b->T_cap * b->B_cap + b->B_cap + 256;
+  if (!make_tmap_2d(&tm_h, b->d_hall, rows, b->e->Cp, b->e->Cp, 128)) return -1;
+  CUDA_OK(cudaLaunchKernelEx(&cfgl, kern, tm_h, b->e->tm_wh, lp));
+  return 0;
+}
+
 int launch_lstm(Batch* b, const sttlstm::LstmParams& lp, int grid, int B, cudaStream_t st) {
   if (B <= 128) return launch_lstm_mt<1, 6>(b, lp, grid, st);
+  const int rc = launch_lstm_pair(b, lp, grid, st);
+  if (rc <= 0) return rc;
   return launch_lstm_mt<2, 5>(b, lp, grid, st);
 }
 
@@ -783,6 +823,7 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
     lp.B = B; lp.T = T; lp.n_cell = Cp; lp.xw = b->d_xw; lp.h_all = b->d_hall; lp.c_state = b->d_c; lp.h_state = b->d_h;
     lp.barrier = b->d_barrier;
     lp.prof = b->d_lstm_prof;
+    lp.debug = getenv("STT_B200_LSTM_DEBUG") ? 1 : 0;
     const int grid = Cp / sttlstm::kCellsPerCta;
     if (launch_lstm(b, lp, grid, B, st)) return -1;
   }

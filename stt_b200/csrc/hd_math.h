@@ -108,7 +108,7 @@ STT_HD double add64(double a, double b) {
 
 // glibc __logf (e_logf.c), FMA-contracted variant.  Special cases return what glibc returns
 // (errno side effects aside): log(+0)=-inf, log(x<0)=nan, log(inf)=inf.
-STT_HD float glibc_logf(float x) {
+STT_HD float glibc_logf_t(float x, const LogfEntry* tab) {
   const double Ln2 = 0x1.62e42fefa39efp-1;
   const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
   uint32_t ix = as_u32(x);
@@ -124,11 +124,7 @@ STT_HD float glibc_logf(float x) {
   int i = (tmp >> 19) & 15;
   int k = (int32_t)tmp >> 23;
   uint32_t iz = ix - (tmp & (0x1ffu << 23));
-#if defined(__CUDA_ARCH__)
-  const double invc = kLogfTabDev[i].invc, logc = kLogfTabDev[i].logc;
-#else
-  const double invc = kLogfTabHost[i].invc, logc = kLogfTabHost[i].logc;
-#endif
+  const double invc = tab[i].invc, logc = tab[i].logc;
   double z = (double)as_f32(iz);
   double r = fma64(z, invc, -1.0);
   double y0 = fma64((double)k, Ln2, logc);
@@ -140,7 +136,7 @@ STT_HD float glibc_logf(float x) {
 }
 
 // glibc __expf (e_expf.c), FMA-contracted variant, non-TOINT_INTRINSICS path (x86-64).
-STT_HD float glibc_expf(float x) {
+STT_HD float glibc_expf_t(float x, const uint64_t* tab) {
   const double InvLn2N = 0x1.71547652b82fep+0 * 32.0;
   const double Shift = 0x1.8p+52;
   const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0, C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0,
@@ -160,11 +156,7 @@ STT_HD float glibc_expf(float x) {
   // glibc's -mfma build contracts the product into this subtraction (pinned exhaustively:
   // with r = z - kd two of the 2^32 inputs differ from libm, with the fma none do).
   double r = fma64(InvLn2N, xd, -kd);
-#if defined(__CUDA_ARCH__)
-  uint64_t t = kExp2fTabDev[ki & 31];
-#else
-  uint64_t t = kExp2fTabHost[ki & 31];
-#endif
+  uint64_t t = tab[ki & 31];
   t += ki << (52 - 5);
   double s = as_f64(t);
   z = fma64(C0, r, C1);
@@ -175,7 +167,42 @@ STT_HD float glibc_expf(float x) {
   return (float)y;
 }
 
+// Default-table wrappers (global-memory tables on the device, static tables on the host).
+STT_HD float glibc_logf(float x) {
+#if defined(__CUDA_ARCH__)
+  return glibc_logf_t(x, kLogfTabDev);
+#else
+  return glibc_logf_t(x, kLogfTabHost);
+#endif
+}
+STT_HD float glibc_expf(float x) {
+#if defined(__CUDA_ARCH__)
+  return glibc_expf_t(x, kExp2fTabDev);
+#else
+  return glibc_expf_t(x, kExp2fTabHost);
+#endif
+}
+
+// The two tables packed for a shared-memory copy (kernels whose serial path is dominated by these functions).
+struct MathTables {
+  LogfEntry logf_tab[16];
+  uint64_t exp2f_tab[32];
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ void load_math_tables(MathTables* dst, int tid, int nthreads) {
+  for (int i = tid; i < 16; i += nthreads) dst->logf_tab[i] = kLogfTabDev[i];
+  for (int i = tid; i < 32; i += nthreads) dst->exp2f_tab[i] = kExp2fTabDev[i];
+}
+#endif
+
 // log_sum_exp<float>, decoder_utils.h:46-53 (num_min = -FLT_MAX).
+STT_HD float log_sum_exp_t(float x, float y, const MathTables* mt) {
+  const float num_min = -3.402823466e+38f;
+  if (x <= num_min) return y;
+  if (y <= num_min) return x;
+  float xmax = x > y ? x : y;  // std::max(x, y): returns x when equal
+  return glibc_logf_t(glibc_expf_t(x - xmax, mt->exp2f_tab) + glibc_expf_t(y - xmax, mt->exp2f_tab), mt->logf_tab) + xmax;
+}
 STT_HD float log_sum_exp(float x, float y) {
   const float num_min = -3.402823466e+38f;
   if (x <= num_min) return y;

@@ -89,3 +89,22 @@ def test_am_probs_full_size_model(oracle, tmp_path):
     err = np.abs(got - probs_ref).max()
     print("full-size model max |dp| = %.3e" % err)
     assert err <= PROBS_ATOL
+
+
+def test_am_large_batch_uses_pair_kernel_and_matches_single(small_model):
+    """129..256 utterances run the cta_group::2 LSTM kernel: every row must equal the batch-of-one result (<= 128
+    utterances, single-CTA kernel) bit for bit -- same fp16 operands, same fp32 accumulation order along K."""
+    from stt_b200 import Model, synth
+    path, _ = small_model
+    m = Model(path)
+    B = 131
+    lens = [8000 if i % 3 else 6000 + 37 * i for i in range(B)]
+    pcms = [synth.make_pcm(n, utt=300 + i) for i, n in enumerate(lens)]
+    b = m.createBatch(B, max(lens))
+    b.upload(pcms)
+    b.forward()
+    b1 = m.createBatch(1, max(lens))
+    for i in (0, 1, 2, 64, 127, 128, 129, 130):
+        b1.upload([pcms[i]])
+        b1.forward()
+        np.testing.assert_array_equal(b.probs(i), b1.probs(0))
