@@ -228,25 +228,22 @@ def main():
     audio_per_step = B * args.seconds * world
     value = audio_per_step / (ms_step * 1e-3)
 
-    # ---- e2e through the C ABI with host buffers (PCM waits in pinned host memory, as the contract allows)
+    # ---- e2e through the C ABI with host buffers (PCM waits in pinned host memory, as the contract allows).
+    #      Two staged batch contexts are kept in flight (stt_b200.BatchPipeline) so that a batch's H2D copy and the host
+    #      work around it overlap the previous batch's kernels; every step still uploads its PCM and fetches its results.
+    from stt_b200 import BatchPipeline
+    E2E_DEPTH = 2
+    pipe = BatchPipeline(model, B, n_samples, depth=E2E_DEPTH)
     pinned = []
-    for u in range(B):
-        hb = batch.host_buffer(u, n_samples)
-        hb[:] = pcms[u]
-        pinned.append(hb)
-
-    def e2e_step():
-        batch.upload(pinned)
-        batch.forward()
-        batch.decode(1)
-        batch.fetch()
-        return batch.transcripts()
-
-    e2e_step()
+    for k in range(E2E_DEPTH):
+        rows = pipe.host_buffers(k, B, n_samples)
+        for u in range(B):
+            rows[u][:] = pcms[u]
+        pinned.append(rows)
+    pipe.map([pinned[i % E2E_DEPTH] for i in range(E2E_DEPTH)])   # warm both contexts
     barrier()
     w0 = time.perf_counter()
-    for _ in range(args.steps):
-        texts = e2e_step()
+    texts = pipe.map([pinned[i % E2E_DEPTH] for i in range(args.steps)])[-1]
     barrier()
     e2e_wall = max_over_ranks((time.perf_counter() - w0) / args.steps)
     e2e_value = audio_per_step / e2e_wall
@@ -292,7 +289,7 @@ def main():
             "data": "synthetic (random-init weights with calibrated CTC-like output layer; phone-sequence PCM)",
             "config": config, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_wall * 1e3},
+                    "ms_per_step": e2e_wall * 1e3, "batches_in_flight": E2E_DEPTH},
             "roofline": roofline, "stages_ms": stages, "roofline_all": roof_all,
             "am_tensor_roofline": {"achieved": am_flops / (am_ms * 1e-3) / 1e12, "peak": tf_sust, "unit": "TFLOP/s",
                                    "frac": am_flops / (am_ms * 1e-3) / 1e12 / tf_sust},

@@ -8,6 +8,7 @@ from .api import (  # noqa: F401
     Model,
     Stream,
     Batch,
+    BatchPipeline,
     CandidateTranscript,
     Metadata,
     TokenMetadata,

@@ -413,7 +413,7 @@ class Batch(object):
     def phase_cycles(self):
         arr = (ctypes.c_ulonglong * 8)()
         lib().STTX_BatchPhaseCycles(self._impl, arr)
-        names = ("gate_cutoff", "child_discovery", "lm", "live_update", "children", "select", "commit", "unused")
+        names = ("cutoff", "parent_lookup", "lm", "live_update", "children", "select", "commit_new_nodes", "compact")
         return dict(zip(names, [int(x) for x in arr]))
 
     def lstm_profile(self):
@@ -461,3 +461,48 @@ class Batch(object):
         self.n = p.shape[0]
         self._ok(lib().STTX_BatchSetProbs(self._impl, p.ctypes.data, t.ctypes.data, p.shape[0], p.shape[1]),
                  "BatchSetProbs")
+
+
+class BatchPipeline(object):
+    """`depth` staged batch contexts driven by one host thread each, so that batch i+1's pinned staging and H2D copy
+    (and the host-side result parsing of batch i-1) overlap batch i's kernels.  Every batch still pays its own
+    upload -> forward -> decode -> fetch; only the waiting is shared.  Results come back in submission order."""
+
+    def __init__(self, model, max_utterances, max_samples, depth=2):
+        self.batches = [Batch(model, max_utterances, max_samples) for _ in range(depth)]
+
+    def host_buffers(self, slot, n_utt, n_samples):
+        return [self.batches[slot].host_buffer(u, n_samples) for u in range(n_utt)]
+
+    @staticmethod
+    def _one(bt, audio_buffers, num_results):
+        bt.upload(audio_buffers)
+        bt.forward()
+        bt.decode(num_results)
+        bt.fetch()
+        return bt.transcripts()
+
+    def map(self, batches_of_audio, num_results=1):
+        """batches_of_audio: sequence of lists of int16 arrays; returns one transcript list per batch, in order.
+        Batch i runs on context i % depth, so callers that pre-fill pinned rows use host_buffers(i % depth, ...)."""
+        import threading
+        items = list(batches_of_audio)
+        out = [None] * len(items)
+        errs = []
+        depth = len(self.batches)
+
+        def worker(k):
+            try:
+                for i in range(k, len(items), depth):
+                    out[i] = self._one(self.batches[k], items[i], num_results)
+            except Exception as ex:  # surfaced to the caller below
+                errs.append(ex)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(min(depth, len(items)))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out

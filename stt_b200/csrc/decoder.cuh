@@ -42,29 +42,30 @@ constexpr int kMaxClasses = 64;
 constexpr int kMaxWordBytes = 128;
 constexpr int kStateWords = sttscorer::kMaxOrder - 1;
 constexpr int kMaxHotWords = 32;
+constexpr int kCommitRounds = 8;   // candidate rounds (of NT) compacted per scan in phase 6
 
 struct Node {            // one surviving prefix (PathTrie node), 32 bytes
   uint32_t parent;       // arena id, kNone for the root
   uint32_t chr;          // label, kRootChar for the root
   int32_t dict;          // dictionary-FST state AFTER this label (already reset to Start() after a final state)
   uint32_t last_space;   // nearest ancestor-or-self whose label is the space, or kNone
-  uint32_t word_id;      // for space nodes: vocabulary id of the word they terminate
+  union {
+    uint32_t word_id;    // space nodes: vocabulary id of the word they terminate
+    uint32_t ord;        // other nodes: ordinal of the partial word's path in the dictionary FST (DecodeParams); root 0
+  };
   uint32_t live_slot;    // index in the current live list, or kNone
   uint32_t lm_wid;       // LM cache valid flag / word id of the word ending here (kNone = not computed)
-  uint32_t pad;
-};
-struct HtSlot {          // (parent node, label) -> node id, open addressing; key 0 = empty
-  unsigned long long key;
-  uint32_t val, pad;
+  uint32_t child_mask;   // labels for which a child node has ever been created
 };
 
 // Per-utterance device state ("stream slot").  All pointers are device memory sized for (beam_cap, t_cap).
 struct Slot {
   Node* nodes;           // [arena_cap]; node 0 is the root
   // A pruned node that still has live descendants must be REVIVED under its old id when its prefix re-enters the beam
-  // (path_trie.cpp:45-52), so that those descendants keep merging into it: every node ever created is findable here.
-  HtSlot* ht;            // [ht_mask + 1], zero-initialised by the host
-  uint32_t ht_mask;
+  // (path_trie.cpp:45-52), so that those descendants keep merging into it: every node ever created stays reachable
+  // from its parent through a first-child / next-sibling list.  Node::child_mask says whether a (parent, label) child
+  // was ever created, so the common case -- a brand-new child -- needs no lookup at all, only a push.
+  uint2* links;          // [arena_cap] {first child, next sibling}
   // Per-node LM cache, keyed by the node that ENDS a word: the natural-log conditional probability of that word given
   // its history (Scorer::get_log_cond_prob's return value), its vocabulary id, and the KenLM state after it.  The
   // reference recomputes the whole <=order-word window on every call (scorer.cpp:307-344, 369-396); scoring the last
@@ -84,6 +85,7 @@ struct Slot {
   // per-step candidates when they do not fit in shared memory, and scratch for finalize; capacity cand_cap
   unsigned long long* c_key;
   uint32_t *c_p0, *c_p1;
+  uint32_t* aux;                     // [4 * beam_cap] see StepSmem::aux
   unsigned long long* phase_cycles;  // [8] instrumentation: SM cycles per phase (thread 0's clock)
   // scalars: 0 n_live, 2 arena_count, 3 ts_count, 4 abs_time_step, 5 start_expanding, 6 overflow,
   //          7 LM words scored (reference-equivalent window sizes), 8 LM calls, 9 max candidates in a step,
@@ -102,6 +104,15 @@ struct DecodeParams {
   // that have an arc}, per arc {ilabel, dictionary state of the child = Start() if the arc's target is final}
   const uint2* fst_state2;
   const int2* fst_arc2;
+  // Word ordinals (perfect hash of the acyclic dictionary FST, built by engine.cu): the words of the FST in
+  // label-lexicographic order are numbered 0..n-1; ordinal(word) = sum over its arcs of arc_skip.  A node carries the
+  // partial sum, so the KenLM id of the word that ends at a node is ONE table read instead of walking the prefix back
+  // to the last space, hashing the bytes and binary-searching the vocabulary (Scorer::make_ngram + Vocabulary::Index,
+  // scorer.cpp:307-344).  Null when the FST is not an acyclic acceptor whose words end with the space label: the
+  // decoder then takes the walking path everywhere.
+  const uint32_t* fst_arc_skip;    // [n_arcs]
+  const uint32_t* fst_space_skip;  // [n_states] skip of the state's space arc when that arc ends a word, else kNone
+  const uint32_t* ord2wid;         // [n_words] KenLM vocabulary id (0 = <unk>)
   // hot words (ctc_beam_search_decoder.cpp:224-236): vocabulary ids and boosts, snapshotted when the stream starts
   int n_hot;
   uint32_t hot_id[kMaxHotWords];
@@ -116,37 +127,15 @@ struct StepInput {
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
-__device__ __forceinline__ uint32_t ht_hash(unsigned long long k) {
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdULL;
-  k ^= k >> 33;
-  return (uint32_t)k;
-}
-__device__ __forceinline__ unsigned long long ht_make_key(uint32_t parent_node, uint32_t c) {
-  return ((unsigned long long)(parent_node + 1u) << 8) | (unsigned long long)(c & 0xffu);
-}
-__device__ __forceinline__ uint32_t ht_find(const Slot& s, unsigned long long key) {
-  uint32_t h = ht_hash(key) & s.ht_mask;
-  for (;;) {
-    const ulonglong2 slot = *reinterpret_cast<const ulonglong2*>(&s.ht[h]);
-    if (slot.x == key) return (uint32_t)slot.y;
-    if (slot.x == 0ull) return kNone;
-    h = (h + 1) & s.ht_mask;
+__device__ __forceinline__ uint32_t child_find(const Slot& s, uint32_t parent, uint32_t c) {
+  uint32_t k = s.links[parent].x;
+  while (k != kNone) {
+    const uint32_t kc = s.nodes[k].chr;
+    const uint32_t nx = s.links[k].y;
+    if (kc == c) return k;
+    k = nx;
   }
-}
-__device__ __forceinline__ void ht_insert(const Slot& s, unsigned long long key, uint32_t val) {
-  uint32_t h = ht_hash(key) & s.ht_mask;
-  for (;;) {
-    // the value is written before the key is published; distinct threads insert distinct keys
-    const unsigned long long prev = atomicCAS(&s.ht[h].key, 0ull, 0xffffffffffffffffull);
-    if (prev == 0ull) {
-      s.ht[h].val = val;
-      __threadfence_block();
-      atomicExch(&s.ht[h].key, key);
-      return;
-    }
-    h = (h + 1) & s.ht_mask;
-  }
+  return kNone;
 }
 __device__ __forceinline__ uint32_t sortable(float f) {
   uint32_t u = __float_as_uint(f);
@@ -212,8 +201,9 @@ __device__ double lm_window_cond(const Slot& s, const sttscorer::ScorerView& v, 
 }
 
 // Cached evaluation of get_log_cond_prob(make_ngram(prefix `node`), bos) -- see Slot::lm_cond.
-__device__ double lm_eval_node(const Slot& s, const sttscorer::ScorerView& v, uint32_t node, uint32_t* word_out,
+__device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t node, uint32_t* word_out,
                                uint32_t* n_window_out) {
+  const sttscorer::ScorerView& v = p.scorer;
   const int order = (int)v.order;
   const Node nd = s.nodes[node];
   if (nd.lm_wid != kNone) {
@@ -235,7 +225,11 @@ __device__ double lm_eval_node(const Slot& s, const sttscorer::ScorerView& v, ui
   } else {
     // ---- the word ending at `node`
     const uint32_t stop = nd.last_space;  // == node when node is itself a space (empty word)
-    if (cc != (uint32_t)v.space_label) {
+    uint32_t sk = kNone;
+    if (cc != (uint32_t)v.space_label && p.fst_space_skip) sk = __ldg(p.fst_space_skip + nd.dict);
+    if (sk != kNone) {
+      wid = __ldg(p.ord2wid + nd.ord + sk);
+    } else if (cc != (uint32_t)v.space_label) {
       uint8_t buf[kMaxWordBytes];
       int len = 0;
       bool too_long = false;
@@ -345,9 +339,10 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start)
   if (u >= n_slots) return;
   Slot& s = slots[u];
   Node root;
-  root.parent = kNone; root.chr = kRootChar; root.dict = fst_start; root.last_space = kNone; root.word_id = 0;
-  root.live_slot = 0; root.lm_wid = kNone; root.pad = 0;
+  root.parent = kNone; root.chr = kRootChar; root.dict = fst_start; root.last_space = kNone; root.ord = 0;
+  root.live_slot = 0; root.lm_wid = kNone; root.child_mask = 0;
   s.nodes[0] = root;
+  s.links[0] = make_uint2(kNone, kNone);
   s.ts_parent[0] = kNone;
   s.ts_val[0] = 0;
   s.score[0] = 0.f;
@@ -410,12 +405,16 @@ struct StepSmem {
   uint32_t lmq[WC];       // LM work list
   uint32_t lmwid[WC];
   float lmterm[WC];
+  // word ordinal + created-children mask of each live prefix, double buffered: [ord0 | ord1 | cmask0 | cmask1].  The
+  // wide-beam instantiation (WC > 512, one CTA per SM) has no room left and keeps them in Slot::aux (global memory).
+  uint32_t aux[WC <= 512 ? 4 * WC : 1];
   unsigned long long key[NC > 0 ? NC : 1];
   uint32_t p0[NC > 0 ? NC : 1], p1[NC > 0 ? NC : 1];
 };
 
 template <int NT, int WC, int NC>
 __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
+  static_assert(NT == 512, "phase 6 assumes 16 warps (kCommitRounds * 16 warp counts scanned by one warp)");
   Slot& s = slots[blockIdx.x];
   const StepInput in = inputs[blockIdx.x];
   const int tid = threadIdx.x;
@@ -429,6 +428,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   __shared__ double s_logblank[2];
   __shared__ uint32_t s_gate[2];
   __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_cnt[kCommitRounds * (NT / 32) + 1];
   __shared__ uint32_t s_warp[NT / 32 + 1];
   __shared__ float s_red[NT / 32];
   __shared__ uint32_t s_u[8];
@@ -448,6 +448,9 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     s_u[7] = 0;
     for (int q = 0; q < 8; ++q) s_ph[q] = 0;
   }
+  uint32_t* const aux_base = (WC <= 512) ? sm.aux : s.aux;
+  uint32_t* const aux_ord[2] = {aux_base, aux_base + WC};
+  uint32_t* const aux_cm[2] = {aux_base + 2 * WC, aux_base + 3 * WC};
   // ---- load the live list left by the previous launch
   int cur = 0;
   for (uint32_t i = tid; i < n_live; i += NT) {
@@ -462,6 +465,8 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     L.pnode[i] = n.parent;
     L.lsp[i] = n.last_space;
     L.dict[i] = n.dict;
+    aux_ord[0][i] = ((int)n.chr == p.space_id && p.has_scorer) ? 0u : n.ord;  // a space node starts a new word
+    aux_cm[0][i] = n.child_mask;
     L.chr[i] = (uint8_t)n.chr;
     uint2 st = make_uint2(0u, all_labels);
     if (p.has_scorer) st = p.fst_state2[n.dict];
@@ -476,6 +481,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     return use64 ? in.probs64[(size_t)row * C + c] : (double)in.probs[(size_t)row * C + c];
   };
   for (uint32_t i = tid; i < (uint32_t)WC; i += NT) sm.child[i] = 0;
+  for (int h = tid; h < 256; h += NT) s_hist[h] = 0;
   if (in.n_steps > 0) {
     // class log-probs of the first row (get_pruned_emissions :328-358 with the C-API's cutoff_prob = 1.0,
     // cutoff_top_n = 40 >= n_classes: no pruning, index order, blank last); later rows are prepared one step ahead
@@ -493,6 +499,10 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   for (int step = 0; step < in.n_steps; ++step, ++abs_t) {
     LiveList<WC>& L = sm.live[cur];
     LiveList<WC>& Nx = sm.live[cur ^ 1];
+    uint32_t* const ordL = cur ? aux_ord[1] : aux_ord[0];
+    uint32_t* const ordN = cur ? aux_ord[0] : aux_ord[1];
+    uint32_t* const cmL = cur ? aux_cm[1] : aux_cm[0];
+    uint32_t* const cmN = cur ? aux_cm[0] : aux_cm[1];
     // ---- phase 0: gate (:125-132), the beam's minimum score, and which (parent, label) pairs already have a live
     //      child.  This row's log-probs were prepared during the previous step; the next row is fetched now and turned
     //      into log-probs at the end of this step, off the critical path.
@@ -522,6 +532,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     if (tid == 0) s_u[1] = 0;  // LM queue length
     start_expanding |= s_gate[cb];
     __syncthreads();
+    PHASE_MARK(1);
     if (!start_expanding || overflow) {
       if (have_next) {
         if (tid < C) s_logp2[cb ^ 1][tid] = sttmath::glibc_logf(next_p + kFltMin);
@@ -546,7 +557,6 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       full_beam = (n_live == (uint32_t)W);
     }
     PHASE_MARK(0);
-    PHASE_MARK(1);
 
     // ---- phase 2b: LM terms of the live prefixes that will be extended by the space this step
     if (p.has_scorer) {
@@ -566,7 +576,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           const uint32_t i = sm.lmq[q];
           uint32_t wid, nw;
           // (float)(cond * alpha): ctc_beam_search_decoder.cpp:239 (hot-word boost = 0)
-          double cond = lm_eval_node(s, sv, L.node[i], &wid, &nw);
+          double cond = lm_eval_node(s, p, L.node[i], &wid, &nw);
           if (p.n_hot > 0) cond += (double)hot_word_boost(s, p, L.node[i], wid);
           sm.lmterm[i] = (float)(cond * sv.alpha);
           sm.lmwid[i] = wid;
@@ -689,24 +699,18 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       const float si = L.score[i];
       const float bp = L.b[i];
       const uint32_t cp = (L.chr[i] == (uint8_t)kRootChar) ? kRootChar : (uint32_t)L.chr[i];
-      const uint32_t mask = L.mask[i], pos = L.pos[i];
       while (allow) {
         const int c = __ffs(allow) - 1;
         allow &= allow - 1;
         float lp;
         if ((uint32_t)c == cp) lp = (bp > kNegMax) ? s_logp[c] + bp : kNegMax;
         else lp = s_logp[c] + si;
-        int32_t nds = 0;
-        if (p.has_scorer) {
-          nds = p.fst_arc2[pos + __popc(mask & ((1u << c) - 1u))].y;
-          if (c == p.space_id) {
-            lp += sm.lmterm[i];
-            lp = (float)((double)lp + sv.beta);
-          }
+        if (p.has_scorer && c == p.space_id) {
+          lp += sm.lmterm[i];
+          lp = (float)((double)lp + sv.beta);
         }
         K[e] = make_key(lp, (uint32_t)c, e);
-        P0[e] = i | ((uint32_t)c << 16);
-        P1[e] = (uint32_t)nds;
+        P0[e] = i | ((uint32_t)c << 16);   // the child's dictionary state is looked up in phase 6, for survivors only
         ++e;
       }
     }
@@ -723,13 +727,12 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     PHASE_MARK(4);
 
     // ---- phase 5: exact top-W radix select on the 64-bit key (:263-274 nth_element + prefix_compare)
+    //      two barriers per pass: warp 0 re-zeroes the histogram right after scanning it
     unsigned long long sel_prefix = 0, sel_mask = 0;
     if (N > (uint32_t)W) {
       uint32_t k_rem = (uint32_t)W;
       for (int pass = 7; pass >= 0; --pass) {
         const int shift = pass * 8;
-        for (int h = tid; h < 256; h += NT) s_hist[h] = 0;
-        __syncthreads();
         for (uint32_t e = tid; e < N; e += NT) {
           const unsigned long long key = K[e];
           if ((key & sel_mask) == sel_prefix) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
@@ -737,9 +740,14 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         __syncthreads();
         if (tid < 32) {
           // lane l owns bins [8l, 8l+8); find the bin where the count from the top crosses k_rem
+          uint32_t hc[8];
           uint32_t mine = 0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) mine += s_hist[tid * 8 + q];
+          for (int q = 0; q < 8; ++q) {
+            hc[q] = s_hist[tid * 8 + q];
+            s_hist[tid * 8 + q] = 0;
+            mine += hc[q];
+          }
           uint32_t suffix = mine;  // inclusive sum over lanes >= tid
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -749,8 +757,9 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           const uint32_t above = suffix - mine;  // elements in higher lanes
           if (above < k_rem && suffix >= k_rem) {
             uint32_t cum = above;
+#pragma unroll
             for (int q = 7; q >= 0; --q) {
-              const uint32_t hcount = s_hist[tid * 8 + q];
+              const uint32_t hcount = hc[q];
               if (cum + hcount >= k_rem) {
                 s_u[2] = (uint32_t)(tid * 8 + q);
                 s_u[3] = k_rem - cum;   // still needed from this bin
@@ -765,9 +774,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         sel_prefix |= (unsigned long long)s_u[2] << shift;
         sel_mask |= (unsigned long long)255u << shift;
         k_rem = s_u[3];
-        const bool done = (s_u[4] == k_rem);  // every element with this prefix is selected
-        __syncthreads();
-        if (done) break;
+        if (s_u[4] == k_rem) break;  // every element with this prefix is selected
       }
     }
     PHASE_MARK(5);
@@ -775,94 +782,154 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     // ---- phase 6: order-preserving compaction + commit (iterate_to_vec :159-190, remove :192-209)
     if (tid == 0) s_u[5] = arena_count;
     // (i) shared-memory-only compaction, in candidate order (live entries precede new ones): survivors get their slot
-    //     in the next live list; a new survivor parks (parent index, label, dictionary state) there.
+    //     in the next live list; a new survivor parks (parent index, label) there.  Up to kCommitRounds rounds of NT
+    //     candidates share ONE scan: per-round warp ballots, a 128-entry scan of the warp counts by warp 0.
     uint32_t out_base = 0;
-    for (uint32_t base = 0; base < N; base += NT) {
-      const uint32_t e = base + tid;
-      unsigned long long key = 0;
-      bool keep = false;
-      if (e < N) {
-        key = K[e];
-        keep = (N <= (uint32_t)W) || ((key & sel_mask) >= sel_prefix);
+    for (uint32_t g0 = 0; g0 < N; g0 += kCommitRounds * NT) {
+      unsigned long long keyq[kCommitRounds];
+      uint32_t bal[kCommitRounds];
+      const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+      for (int q = 0; q < kCommitRounds; ++q) {
+        const uint32_t e = g0 + (uint32_t)q * NT + tid;
+        unsigned long long key = 0;
+        bool keep = false;
+        if (e < N) {
+          key = K[e];
+          keep = (N <= (uint32_t)W) || ((key & sel_mask) >= sel_prefix);
+        }
+        keyq[q] = key;
+        bal[q] = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_cnt[q * (NT / 32) + warp] = __popc(bal[q]);
       }
-      uint32_t total;
-      const uint32_t pos = out_base + block_scan<NT>(keep ? 1u : 0u, s_warp, total);
-      if (e < n_live) {
-        const uint32_t nd = L.node[e];
-        if (keep) {
-          Nx.score[pos] = unsortable((uint32_t)(key >> 32));
-          Nx.b[pos] = __uint_as_float(P0[e]);
-          Nx.nb[pos] = __uint_as_float(P1[e]);
-          Nx.node[pos] = nd;
-          Nx.pnode[pos] = L.pnode[e];
-          Nx.lsp[pos] = L.lsp[e];
-          Nx.pos[pos] = L.pos[e];
-          Nx.mask[pos] = L.mask[e];
-          Nx.dict[pos] = L.dict[e];
-          Nx.chr[pos] = L.chr[e];
-          const uint32_t tp = sm.tsprev[e];
-          if (tp != kNone) {
-            const uint32_t id = ts_count + pos;
-            if (id < s.ts_cap) { s.ts_parent[id] = tp; s.ts_val[id] = abs_t; }
-            Nx.ts[pos] = id;
+      __syncthreads();
+      if (warp == 0) {
+        constexpr int PER = kCommitRounds * (NT / 32) / 32;  // entries per lane
+        uint32_t v[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { v[i] = s_cnt[lane * PER + i]; sum += v[i]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += o;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { s_cnt[lane * PER + i] = run; run += v[i]; }
+        if (lane == 31) s_cnt[kCommitRounds * (NT / 32)] = incl;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < kCommitRounds; ++q) {
+        const uint32_t e = g0 + (uint32_t)q * NT + tid;
+        if (e >= N) break;
+        const bool keep = (bal[q] >> lane) & 1u;
+        const uint32_t pos = out_base + s_cnt[q * (NT / 32) + warp] + __popc(bal[q] & ((1u << lane) - 1u));
+        const unsigned long long key = keyq[q];
+        if (e < n_live) {
+          const uint32_t nd = L.node[e];
+          if (keep) {
+            Nx.score[pos] = unsortable((uint32_t)(key >> 32));
+            Nx.b[pos] = __uint_as_float(P0[e]);
+            Nx.nb[pos] = __uint_as_float(P1[e]);
+            Nx.node[pos] = nd;
+            Nx.pnode[pos] = L.pnode[e];
+            Nx.lsp[pos] = L.lsp[e];
+            Nx.pos[pos] = L.pos[e];
+            Nx.mask[pos] = L.mask[e];
+            ordN[pos] = ordL[e];
+            cmN[pos] = cmL[e];
+            Nx.dict[pos] = L.dict[e];
+            Nx.chr[pos] = L.chr[e];
+            const uint32_t tp = sm.tsprev[e];
+            if (tp != kNone) {
+              const uint32_t id = ts_count + pos;
+              if (id < s.ts_cap) { s.ts_parent[id] = tp; s.ts_val[id] = abs_t; }
+              Nx.ts[pos] = id;
+            } else {
+              Nx.ts[pos] = L.ts[e];
+            }
+            s.nodes[nd].live_slot = pos;
+            sm.lmq[pos] = kNone;  // not a new node
+            sm.plive[e] = pos;    // old live index -> new live index, for the children created below
           } else {
-            Nx.ts[pos] = L.ts[e];
+            s.nodes[nd].live_slot = kNone;
+            sm.plive[e] = kNone;
           }
-          s.nodes[nd].live_slot = pos;
-          sm.lmq[pos] = kNone;  // not a new node
-        } else {
-          s.nodes[nd].live_slot = kNone;
+        } else if (keep) {
+          const float lp = unsortable((uint32_t)(key >> 32));
+          Nx.score[pos] = lp;
+          Nx.b[pos] = kNegMax;
+          Nx.nb[pos] = lp;
+          sm.lmq[pos] = P0[e];  // parent live index | label << 16
         }
-      } else if (e < N && keep) {
-        const float lp = unsortable((uint32_t)(key >> 32));
-        Nx.score[pos] = lp;
-        Nx.b[pos] = kNegMax;
-        Nx.nb[pos] = lp;
-        Nx.dict[pos] = (int32_t)P1[e];
-        sm.lmq[pos] = P0[e];  // parent live index | label << 16
       }
-      out_base += total;
+      out_base += s_cnt[kCommitRounds * (NT / 32)];
+      __syncthreads();
     }
-    __syncthreads();
-    // (ii) one thread per NEW survivor does the global-memory work (hash lookup / arena node / FST state / timestep
-    //      node), so all those latencies overlap instead of being paid once per 512-candidate round
-    for (uint32_t pos = tid; pos < out_base; pos += NT) {
-      const uint32_t pk = sm.lmq[pos];
-      if (pk == kNone) continue;
-      const uint32_t pi = pk & 0xffffu, c = pk >> 16;
-      const int32_t nds = Nx.dict[pos];
-      const float lp = Nx.score[pos];
-      const uint32_t pnode = L.node[pi];
-      const unsigned long long hk = ht_make_key(pnode, c);
+    PHASE_MARK(7);
+    // (ii) one thread per NEW survivor does the global-memory work (dictionary arc / child lookup / arena node / FST
+    //      state / timestep node), so all those latencies overlap instead of being paid once per 512-candidate round.
+    //      Lookups of previously created children (rare) finish before any list is modified.
+    for (uint32_t base = 0; base < out_base; base += NT) {
+      const uint32_t pos = base + tid;
+      const uint32_t pk = (pos < out_base) ? sm.lmq[pos] : kNone;
+      const bool active = (pk != kNone);
+      const uint32_t pi = pk & 0xffffu, c = (pk >> 16) & 0xffu;
+      uint32_t id = kNone, pnode = kNone, cord = 0, own_mask = 0;
+      int32_t nds = 0;
       uint2 st = make_uint2(0u, all_labels);
-      if (p.has_scorer) st = p.fst_state2[nds];
-      uint32_t id = ht_find(s, hk);
       const bool is_space = ((int)c == p.space_id);
-      if (id == kNone) {
-        id = atomicAdd(&s_u[5], 1u);  // fresh arena node
-        if (id < s.arena_cap) {
-          Node n;
-          n.parent = pnode; n.chr = c; n.dict = nds; n.last_space = is_space ? id : L.lsp[pi];
-          n.word_id = (is_space && p.has_scorer) ? sm.lmwid[pi] : 0u;
-          n.live_slot = pos; n.lm_wid = kNone; n.pad = 0;
-          s.nodes[id] = n;
-          ht_insert(s, hk, id);
+      if (active) {
+        pnode = L.node[pi];
+        if (p.has_scorer) {
+          const uint32_t ai = L.pos[pi] + __popc(L.mask[pi] & ((1u << c) - 1u));
+          nds = __ldg(&p.fst_arc2[ai]).y;
+          if (p.fst_arc_skip && !is_space) cord = ordL[pi] + __ldg(p.fst_arc_skip + ai);
+          st = __ldg(&p.fst_state2[nds]);
         }
-      } else {
-        s.nodes[id].live_slot = pos;  // revived under its old identity
+        if ((cmL[pi] >> c) & 1u) {
+          id = child_find(s, pnode, c);
+          if (id != kNone) own_mask = s.nodes[id].child_mask;
+        }
       }
-      Nx.node[pos] = id;
-      Nx.pnode[pos] = pnode;
-      Nx.lsp[pos] = is_space ? id : L.lsp[pi];
-      Nx.chr[pos] = (uint8_t)c;
-      Nx.pos[pos] = st.x;
-      Nx.mask[pos] = st.y;
-      if (lp > kNegMax) {  // "prefix_new->log_prob_nb_cur < log_p" (:246-251)
-        const uint32_t tid2 = ts_count + pos;
-        if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L.ts[pi]; s.ts_val[tid2] = abs_t; }
-        Nx.ts[pos] = tid2;
-      } else {
-        Nx.ts[pos] = kNone;
+      __syncthreads();
+      if (active) {
+        const float lp = Nx.score[pos];
+        if (id == kNone) {
+          id = atomicAdd(&s_u[5], 1u);  // fresh arena node
+          if (id < s.arena_cap) {
+            const uint32_t old_head = atomicExch(&s.links[pnode].x, id);
+            atomicOr(&s.nodes[pnode].child_mask, 1u << c);
+            Node n;
+            n.parent = pnode; n.chr = c; n.dict = nds; n.last_space = is_space ? id : L.lsp[pi];
+            n.word_id = is_space ? (p.has_scorer ? sm.lmwid[pi] : 0u) : cord;
+            n.live_slot = pos; n.lm_wid = kNone; n.child_mask = 0;
+            s.nodes[id] = n;
+            const uint32_t np = sm.plive[pi];   // the parent's slot in the next live list, if it survived
+            if (np != kNone) atomicOr(&cmN[np], 1u << c);
+            s.links[id] = make_uint2(kNone, old_head);
+          }
+        } else {
+          s.nodes[id].live_slot = pos;  // revived under its old identity
+        }
+        Nx.node[pos] = id;
+        Nx.pnode[pos] = pnode;
+        Nx.lsp[pos] = is_space ? id : L.lsp[pi];
+        Nx.chr[pos] = (uint8_t)c;
+        Nx.dict[pos] = nds;
+        ordN[pos] = cord;    // 0 for a space node: the next word starts here
+        cmN[pos] = own_mask;
+        Nx.pos[pos] = st.x;
+        Nx.mask[pos] = st.y;
+        if (lp > kNegMax) {  // "prefix_new->log_prob_nb_cur < log_p" (:246-251)
+          const uint32_t tid2 = ts_count + pos;
+          if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L.ts[pi]; s.ts_val[tid2] = abs_t; }
+          Nx.ts[pos] = tid2;
+        } else {
+          Nx.ts[pos] = kNone;
+        }
       }
     }
     const uint32_t n_surv = out_base;
@@ -931,7 +998,7 @@ __global__ void __launch_bounds__(NT) decoder_finalize_kernel(Slot* slots, const
     const uint32_t c = s.nodes[nd].chr;
     if (p.has_scorer && i < (uint32_t)p.beam && c != kRootChar && (int)c != p.space_id) {
       uint32_t wid_unused, nw_unused;
-      float add = (float)(lm_eval_node(s, p.scorer, nd, &wid_unused, &nw_unused) * p.scorer.alpha);
+      float add = (float)(lm_eval_node(s, p, nd, &wid_unused, &nw_unused) * p.scorer.alpha);
       add = (float)((double)add + p.scorer.beta);
       sc = sc + add;
     }

@@ -144,6 +144,9 @@ struct Engine {
   sttscorer::ScorerView scorer_view{};
   uint2* fst_state2 = nullptr;  // per state {first arc, label mask}
   int2* fst_arc2 = nullptr;     // per arc {ilabel, child dictionary state}
+  uint32_t* fst_arc_skip = nullptr;    // word-ordinal tables (decoder.cuh DecodeParams), null when not applicable
+  uint32_t* fst_space_skip = nullptr;
+  uint32_t* ord2wid = nullptr;
 };
 
 const sttmodel::HostModel& engine_model(const Engine* e) { return e->hm; }
@@ -328,6 +331,10 @@ void engine_clear_scorer(Engine* e) {
   if (e->scorer_blob) cudaFree(e->scorer_blob);
   if (e->fst_state2) cudaFree(e->fst_state2);
   if (e->fst_arc2) cudaFree(e->fst_arc2);
+  if (e->fst_arc_skip) cudaFree(e->fst_arc_skip);
+  if (e->fst_space_skip) cudaFree(e->fst_space_skip);
+  if (e->ord2wid) cudaFree(e->ord2wid);
+  e->fst_arc_skip = e->fst_space_skip = e->ord2wid = nullptr;
   e->scorer_blob = nullptr;
   e->fst_state2 = nullptr;
   e->fst_arc2 = nullptr;
@@ -342,6 +349,120 @@ void engine_destroy(Engine* e) {
                   (void*)e->b1, (void*)e->b2, (void*)e->b3, (void*)e->bx, (void*)e->b5, (void*)e->b6})
     if (p) cudaFree(p);
   delete e;
+}
+
+// Word ordinals of the dictionary FST (decoder.cuh DecodeParams::fst_arc_skip).  The reference builds the dictionary by
+// adding every vocabulary word + the space label as a path and minimising (scorer.cpp:398-440,
+// decoder_utils.cpp add_word_to_dictionary): an acyclic deterministic acceptor.  With paths(q) = number of accepting
+// paths out of q, arc_skip(q, a) = [q final] + sum of paths(target) over q's arcs with a smaller label, and the sum of
+// arc_skip along a word's arcs is its rank among the FST's words in label order.  ord2wid maps that rank to the KenLM
+// vocabulary id of the word's bytes (the same vocab_index the walking path calls).  Anything unexpected -- a cycle, a
+// word that does not end with the space label, more than 2^31 words -- leaves the tables null (walking path).
+void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_t* bytes) {
+  const int64_t nS = v.fst_nstates, nA = v.fst_narcs;
+  if (nS <= 0 || nA <= 0 || v.fst_start < 0 || v.fst_start >= nS) return;
+  struct Arc { int32_t il, nx; };
+  auto state_arcs = [&](int64_t q, uint32_t* pos, uint32_t* narcs) {
+    const uint8_t* srec = bytes + v.fst_states_off + (uint64_t)q * 20;
+    memcpy(pos, srec + 4, 4);
+    memcpy(narcs, srec + 8, 4);
+  };
+  auto arc_at = [&](uint64_t i) {
+    Arc a;
+    const uint8_t* arc = bytes + v.fst_arcs_off + i * 16;
+    memcpy(&a.il, arc, 4);
+    memcpy(&a.nx, arc + 12, 4);
+    return a;
+  };
+  std::vector<uint64_t> paths((size_t)nS, 0);
+  std::vector<uint8_t> color((size_t)nS, 0);  // 0 new, 1 on the stack, 2 done
+  std::vector<uint32_t> skip((size_t)nA, 0), space_skip((size_t)nS, 0xffffffffu);
+  // iterative post-order DFS from the start state
+  struct Frame { int64_t q; uint32_t pos, narcs, a; uint64_t acc; };
+  std::vector<Frame> stack;
+  auto push = [&](int64_t q) {
+    Frame f; f.q = q; f.a = 0;
+    state_arcs(q, &f.pos, &f.narcs);
+    f.acc = sttscorer::fst_is_final(v, q) ? 1 : 0;
+    color[(size_t)q] = 1;
+    stack.push_back(f);
+  };
+  push(v.fst_start);
+  while (!stack.empty()) {
+    Frame& f = stack.back();
+    if (f.a < f.narcs) {
+      const Arc a = arc_at((uint64_t)f.pos + f.a);
+      if (a.nx < 0 || a.nx >= nS || (uint64_t)f.pos + f.a >= (uint64_t)nA) return;
+      if (color[(size_t)a.nx] == 1) return;  // cycle
+      if (color[(size_t)a.nx] == 0) { push(a.nx); continue; }
+      skip[(size_t)f.pos + f.a] = (uint32_t)f.acc;
+      f.acc += paths[(size_t)a.nx];
+      if (f.acc >= (1ull << 31)) return;
+      ++f.a;
+    } else {
+      paths[(size_t)f.q] = f.acc;
+      color[(size_t)f.q] = 2;
+      stack.pop_back();
+    }
+  }
+  const uint64_t n_words = paths[(size_t)v.fst_start];
+  if (n_words == 0) return;
+  // enumerate the words: ordinal -> vocabulary id; every word must end with the space label on an arc into a final state
+  std::vector<uint32_t> o2w((size_t)n_words, 0);
+  struct EFrame { int64_t q; uint32_t pos, narcs, a; uint32_t ord; size_t len; };
+  std::vector<EFrame> es;
+  std::vector<uint8_t> word;
+  auto epush = [&](int64_t q, uint32_t ord) {
+    EFrame f; f.q = q; f.a = 0; f.ord = ord; f.len = word.size();
+    state_arcs(q, &f.pos, &f.narcs);
+    es.push_back(f);
+  };
+  epush(v.fst_start, 0);
+  uint64_t seen = 0;
+  while (!es.empty()) {
+    EFrame& f = es.back();
+    if (f.a == 0 && f.q != v.fst_start && sttscorer::fst_is_final(v, f.q) && f.narcs != 0) return;  // words nest past a final state
+    if (f.a < f.narcs) {
+      const uint64_t ai = (uint64_t)f.pos + f.a;
+      const Arc a = arc_at(ai);
+      ++f.a;
+      word.resize(f.len);
+      const int label = a.il - 1;
+      if (label < 0 || label >= 256) return;
+      const uint32_t ord = f.ord + skip[(size_t)ai];
+      if (sttscorer::fst_is_final(v, a.nx)) {
+        if ((uint32_t)label != v.space_label) return;
+        uint32_t tp, tn;
+        state_arcs(a.nx, &tp, &tn);
+        if (tn != 0 || ord >= n_words) return;
+        o2w[ord] = sttscorer::vocab_index(v, word.data(), (uint32_t)word.size());
+        space_skip[(size_t)f.q] = skip[(size_t)ai];
+        ++seen;
+      } else {
+        if ((uint32_t)label == v.space_label) return;
+        for (int b = 0; b < v.label_len[label]; ++b) word.push_back(v.label_bytes[label][b]);
+        if (word.size() > 4096) return;
+        epush(a.nx, ord);
+      }
+    } else {
+      es.pop_back();
+    }
+  }
+  if (seen != n_words) return;
+  if (cudaMalloc(reinterpret_cast<void**>(&e->fst_arc_skip), skip.size() * 4) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&e->fst_space_skip), space_skip.size() * 4) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&e->ord2wid), o2w.size() * 4) != cudaSuccess) {
+    cudaGetLastError();
+    if (e->fst_arc_skip) cudaFree(e->fst_arc_skip);
+    if (e->fst_space_skip) cudaFree(e->fst_space_skip);
+    if (e->ord2wid) cudaFree(e->ord2wid);
+    e->fst_arc_skip = e->fst_space_skip = e->ord2wid = nullptr;
+    return;
+  }
+  cudaMemcpy(e->fst_arc_skip, skip.data(), skip.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(e->fst_space_skip, space_skip.data(), space_skip.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(e->ord2wid, o2w.data(), o2w.size() * 4, cudaMemcpyHostToDevice);
+  if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] dictionary word ordinals: %llu words\n", (unsigned long long)n_words);
 }
 
 int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
@@ -390,6 +511,7 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
       return sttscorer::SCORER_UNREADABLE;
     cudaMemcpy(e->fst_state2, st2.data(), st2.size() * sizeof(uint2), cudaMemcpyHostToDevice);
     cudaMemcpy(e->fst_arc2, ar2.data(), ar2.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    build_word_ordinals(e, v, bytes);
   }
   v.blob = e->scorer_blob;
   e->scorer_view = v;
@@ -463,8 +585,6 @@ int alloc_slots(Batch* b) {
   const uint32_t arena_cap = 1u + (uint32_t)W * (uint32_t)b->dec_T_cap;
   const uint32_t ts_cap = 1u + (uint32_t)W * (uint32_t)(b->dec_T_cap + 1);
   const uint32_t cand_cap = (uint32_t)W * (uint32_t)C;
-  uint32_t ht = 1;
-  while (ht < 2u * arena_cap) ht <<= 1;
   // carve one slab per slot
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -474,13 +594,13 @@ int alloc_slots(Batch* b) {
   };
   const int SW = sttdec::kStateWords;
   const size_t o_nodes = take(sizeof(sttdec::Node) * (size_t)arena_cap);
-  const size_t o_ht = take(sizeof(sttdec::HtSlot) * (size_t)ht);
+  const size_t o_links = take(sizeof(uint2) * (size_t)arena_cap);
   const size_t o_lmc = take(8ull * arena_cap), o_lmsw = take(4ull * arena_cap * SW), o_lmsb = take(4ull * arena_cap * SW);
   const size_t o_lmm = take(4ull * arena_cap);
   const size_t o_tsp = take(4ull * ts_cap), o_tsv = take(4ull * ts_cap);
   const size_t o_sc = take(4ull * W), o_bp = take(4ull * W), o_nb = take(4ull * W), o_nd = take(4ull * W), o_lts = take(4ull * W);
   const size_t o_ck = take(8ull * cand_cap), o_p0 = take(4ull * cand_cap), o_p1 = take(4ull * cand_cap);
-  const size_t o_scal = take(64), o_ph = take(64);
+  const size_t o_scal = take(64), o_ph = take(64), o_aux = take(W > 512 ? 16ull * 2048 : 256);  // StepSmem::aux of the wide instantiation (WC = 2048)
   b->slot_bytes = off;
   CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_slot_mem), b->slot_bytes * b->B_cap));
   b->h_slots.resize(b->B_cap);
@@ -488,14 +608,14 @@ int alloc_slots(Batch* b) {
     uint8_t* base = b->d_slot_mem + b->slot_bytes * u;
     sttdec::Slot& s = b->h_slots[u];
     s.nodes = (sttdec::Node*)(base + o_nodes);
-    s.ht = (sttdec::HtSlot*)(base + o_ht);
-    s.ht_mask = ht - 1;
+    s.links = (uint2*)(base + o_links);
     s.lm_cond = (double*)(base + o_lmc); s.lm_sw = (uint32_t*)(base + o_lmsw); s.lm_sb = (float*)(base + o_lmsb);
     s.lm_meta = (uint32_t*)(base + o_lmm);
     s.ts_parent = (uint32_t*)(base + o_tsp); s.ts_val = (uint32_t*)(base + o_tsv);
     s.score = (float*)(base + o_sc); s.b_prev = (float*)(base + o_bp); s.nb_prev = (float*)(base + o_nb);
     s.node = (uint32_t*)(base + o_nd); s.ts = (uint32_t*)(base + o_lts);
     s.c_key = (unsigned long long*)(base + o_ck); s.c_p0 = (uint32_t*)(base + o_p0); s.c_p1 = (uint32_t*)(base + o_p1);
+    s.aux = (uint32_t*)(base + o_aux);
     s.scalars = (uint32_t*)(base + o_scal); s.phase_cycles = (unsigned long long*)(base + o_ph);
     s.arena_cap = arena_cap; s.ts_cap = ts_cap; s.beam_cap = W; s.cand_cap = cand_cap;
   }
@@ -892,6 +1012,9 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
   if (e->has_scorer) dp.scorer = e->scorer_view;
   dp.fst_state2 = e->fst_state2;
   dp.fst_arc2 = e->fst_arc2;
+  dp.fst_arc_skip = getenv("STT_B200_NO_WORD_ORDINALS") ? nullptr : e->fst_arc_skip;
+  dp.fst_space_skip = dp.fst_arc_skip ? e->fst_space_skip : nullptr;
+  dp.ord2wid = dp.fst_arc_skip ? e->ord2wid : nullptr;
   dp.n_hot = e->has_scorer ? (int)std::min<size_t>(b->hot_ids.size(), sttdec::kMaxHotWords) : 0;
   for (int h = 0; h < dp.n_hot; ++h) {
     dp.hot_id[h] = b->hot_ids[h];
@@ -902,9 +1025,6 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
 
 int decoder_reset(Batch* b, int n_slots) {
   cudaStream_t st = b->st;
-  // hash tables must start empty
-  for (int u = 0; u < n_slots; ++u)
-    CUDA_OK(cudaMemsetAsync(b->h_slots[u].ht, 0, sizeof(sttdec::HtSlot) * ((size_t)b->h_slots[u].ht_mask + 1), st));
   const int32_t fst_start = b->e->has_scorer ? (int32_t)b->e->scorer_view.fst_start : 0;
   sttdec::decoder_init_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b->d_slots, n_slots, fst_start);
   CUDA_OK(cudaGetLastError());

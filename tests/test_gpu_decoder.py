@@ -50,6 +50,26 @@ def test_decoder_with_scorer_matches_reference(ref_decoder, small_model, vocab_w
         _compare(b.results(u), ref, "beam=%d T=%d utt=%d" % (beam, T, u))
 
 
+@pytest.mark.parametrize("beam", [700, 2000])
+def test_wide_beam_matches_reference(ref_decoder, small_model, vocab_words, english, beam):
+    """Beam widths above 512 (BASELINE config 5 sweeps to 2000) run the wide instantiation of the step kernel: one CTA
+    per SM, candidates and the word-ordinal / child-mask arrays in global memory."""
+    from stt_b200 import synth
+    o = ref_decoder
+    alpha = o.RefAlphabet(english)
+    sc = o.RefScorer(SCORER, alpha)
+    m = _model(small_model, beam)
+    B, T = 3, 60
+    probs = np.stack([synth.make_ctc_probs(vocab_words, T, utt=7000 + beam + u) for u in range(B)])
+    b = m.createBatch(B, T * 320)
+    b.set_probs(probs, [T] * B)
+    b.decode(num_results=2)
+    b.fetch()
+    for u in range(B):
+        ref = o.ref_decode(probs[u], alpha, beam, sc, num_results=2)
+        _compare(b.results(u), ref, "wide beam=%d utt=%d" % (beam, u))
+
+
 @pytest.mark.parametrize("beam", [4, 64])
 def test_decoder_without_scorer_matches_reference(ref_decoder, small_model, vocab_words, english, beam):
     from stt_b200 import synth
