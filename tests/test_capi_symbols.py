@@ -12,7 +12,7 @@ from conftest import ROOT, _have_gpu
 
 def _declared():
     hdr = open(os.path.join(ROOT, "include", "stt_capi.h")).read()
-    return sorted(set(re.findall(r"STT_EXPORT[^;(]*?\b(STTX?_[A-Za-z]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"STT_EXPORT[^;(]*?\b(STTX?_[A-Za-z0-9]+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():
