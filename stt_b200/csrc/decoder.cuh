@@ -62,10 +62,12 @@ struct Node {            // one surviving prefix (PathTrie node), 32 bytes
 struct Slot {
   Node* nodes;           // [arena_cap]; node 0 is the root
   // A pruned node that still has live descendants must be REVIVED under its old id when its prefix re-enters the beam
-  // (path_trie.cpp:45-52), so that those descendants keep merging into it: every node ever created stays reachable
-  // from its parent through a first-child / next-sibling list.  Node::child_mask says whether a (parent, label) child
-  // was ever created, so the common case -- a brand-new child -- needs no lookup at all, only a push.
-  uint2* links;          // [arena_cap] {first child, next sibling}
+  // (path_trie.cpp:45-52), so that those descendants keep merging into it: every node ever created is findable in
+  // a (parent, label) -> node hash table.  Node::child_mask says whether a (parent, label) child was ever created, so
+  // the common case -- a brand-new child -- needs no lookup at all, only an insert (one atomicMax, see ht_insert).
+  unsigned long long* ht;  // [ht_mask + 1] packed {generation:8 | parent:24 | label:8 | node:24}; stale generation = empty
+  uint32_t ht_mask;
+  uint32_t ht_gen;         // 1..255, bumped by the host on every reset (tables are cleared when it wraps)
   // Per-node LM cache, keyed by the node that ENDS a word: the natural-log conditional probability of that word given
   // its history (Scorer::get_log_cond_prob's return value), its vocabulary id, and the KenLM state after it.  The
   // reference recomputes the whole <=order-word window on every call (scorer.cpp:307-344, 369-396); scoring the last
@@ -103,14 +105,13 @@ struct DecodeParams {
   // dictionary FST, pre-digested on the host (engine.cu build_fst_tables): per state {first arc, bit mask of the labels
   // that have an arc}, per arc {ilabel, dictionary state of the child = Start() if the arc's target is final}
   const uint2* fst_state2;
-  const int2* fst_arc2;
+  const int4* fst_arc4;            // per arc {child state, child's first arc, child's label mask, word-ordinal skip}
   // Word ordinals (perfect hash of the acyclic dictionary FST, built by engine.cu): the words of the FST in
-  // label-lexicographic order are numbered 0..n-1; ordinal(word) = sum over its arcs of arc_skip.  A node carries the
+  // label-lexicographic order are numbered 0..n-1; ordinal(word) = sum over its arcs of fst_arc4[].w.  A node carries the
   // partial sum, so the KenLM id of the word that ends at a node is ONE table read instead of walking the prefix back
   // to the last space, hashing the bytes and binary-searching the vocabulary (Scorer::make_ngram + Vocabulary::Index,
   // scorer.cpp:307-344).  Null when the FST is not an acyclic acceptor whose words end with the space label: the
   // decoder then takes the walking path everywhere.
-  const uint32_t* fst_arc_skip;    // [n_arcs]
   const uint32_t* fst_space_skip;  // [n_states] skip of the state's space arc when that arc ends a word, else kNone
   const uint32_t* ord2wid;         // [n_words] KenLM vocabulary id (0 = <unk>)
   // hot words (ctc_beam_search_decoder.cpp:224-236): vocabulary ids and boosts, snapshotted when the stream starts
@@ -127,15 +128,49 @@ struct StepInput {
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
-__device__ __forceinline__ uint32_t child_find(const Slot& s, uint32_t parent, uint32_t c) {
-  uint32_t k = s.links[parent].x;
-  while (k != kNone) {
-    const uint32_t kc = s.nodes[k].chr;
-    const uint32_t nx = s.links[k].y;
-    if (kc == c) return k;
-    k = nx;
+// (parent, label) -> node.  One 64-bit word per entry, generation in the top byte, so that
+//   * a slot left over from an earlier decode (lower generation) reads as empty -- no per-decode memset of the tables;
+//   * an insert is a single atomicMax: against an empty/stale slot it simply wins.  Against a live entry of the current
+//     generation the larger word stays and the thread carries the smaller one to the next slot (linear probing; an entry
+//     only ever moves forward along its own probe path, so "present between the home slot and the first empty slot"
+//     keeps holding).
+// Lookups happen only for children that are known to exist (Node::child_mask), so a lookup that runs into an empty slot
+// has met an entry in transit between two slots and simply starts over.
+__device__ __forceinline__ uint32_t ht_hash(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+__device__ __forceinline__ unsigned long long ht_pack(uint32_t gen, uint32_t parent, uint32_t c, uint32_t node) {
+  return ((unsigned long long)gen << 56) | ((unsigned long long)(parent & 0xffffffu) << 32) |
+         ((unsigned long long)(c & 0xffu) << 24) | (unsigned long long)(node & 0xffffffu);
+}
+__device__ __forceinline__ void ht_insert(const Slot& s, uint32_t parent, uint32_t c, uint32_t node) {
+  unsigned long long w = ht_pack(s.ht_gen, parent, c, node);
+  uint32_t h = ht_hash(w >> 24) & s.ht_mask;
+  for (;;) {
+    const unsigned long long old = atomicMax(&s.ht[h], w);
+    if ((uint32_t)(old >> 56) != s.ht_gen) return;  // the slot was empty or stale
+    if (old > w) {
+      // the resident entry stays; ours moves on
+    } else {
+      w = old;  // we displaced the resident entry: carry it forward
+    }
+    h = (h + 1) & s.ht_mask;
   }
-  return kNone;
+}
+__device__ __forceinline__ uint32_t ht_find_existing(const Slot& s, uint32_t parent, uint32_t c) {
+  const unsigned long long key = ht_pack(s.ht_gen, parent, c, 0) >> 24;
+  for (;;) {
+    uint32_t h = ht_hash(key) & s.ht_mask;
+    for (;;) {
+      const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&s.ht[h]);
+      if ((w >> 24) == key) return (uint32_t)(w & 0xffffffu);
+      if ((uint32_t)(w >> 56) != s.ht_gen) break;  // in transit: retry from the home slot
+      h = (h + 1) & s.ht_mask;
+    }
+  }
 }
 __device__ __forceinline__ uint32_t sortable(float f) {
   uint32_t u = __float_as_uint(f);
@@ -205,12 +240,15 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
                                uint32_t* n_window_out) {
   const sttscorer::ScorerView& v = p.scorer;
   const int order = (int)v.order;
+  // the three loads are independent: a cached node costs one round trip
+  const uint32_t meta0 = s.lm_meta[node];   // kNone = not computed yet
+  const double cond0 = s.lm_cond[node];
   const Node nd = s.nodes[node];
-  if (nd.lm_wid != kNone) {
+  if (meta0 != kNone) {
     *word_out = nd.lm_wid;
-    const uint32_t nw = s.lm_meta[node] >> 16;
+    const uint32_t nw = meta0 >> 16;
     *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
-    return s.lm_cond[node];
+    return cond0;
   }
   const uint32_t cc = nd.chr;
   double cond;
@@ -334,7 +372,7 @@ __device__ float hot_word_boost(const Slot& s, const DecodeParams& p, uint32_t n
 
 // ------------------------------------------------------------------------------------------------ init
 // DecoderState::init (:22-61): root prefix with score = log_prob_b_prev = 0.
-__global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start) {
+__global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start, uint32_t ht_gen) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= n_slots) return;
   Slot& s = slots[u];
@@ -342,7 +380,8 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start)
   root.parent = kNone; root.chr = kRootChar; root.dict = fst_start; root.last_space = kNone; root.ord = 0;
   root.live_slot = 0; root.lm_wid = kNone; root.child_mask = 0;
   s.nodes[0] = root;
-  s.links[0] = make_uint2(kNone, kNone);
+  s.lm_meta[0] = kNone;
+  s.ht_gen = ht_gen;
   s.ts_parent[0] = kNone;
   s.ts_val[0] = 0;
   s.score[0] = 0.f;
@@ -415,9 +454,12 @@ struct StepSmem {
 template <int NT, int WC, int NC>
 __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
   static_assert(NT == 512, "phase 6 assumes 16 warps (kCommitRounds * 16 warp counts scanned by one warp)");
-  Slot& s = slots[blockIdx.x];
-  const StepInput in = inputs[blockIdx.x];
+  __shared__ Slot s_slot;   // the slot's pointers and capacities are read all over the step loop
   const int tid = threadIdx.x;
+  if (tid < (int)(sizeof(Slot) / 4)) reinterpret_cast<uint32_t*>(&s_slot)[tid] = reinterpret_cast<const uint32_t*>(&slots[blockIdx.x])[tid];
+  __syncthreads();
+  const Slot& s = s_slot;
+  const StepInput in = inputs[blockIdx.x];
   const int C = p.n_classes;
   const int blank = C - 1;
   const int W = p.beam;
@@ -428,6 +470,8 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   __shared__ double s_logblank[2];
   __shared__ uint32_t s_gate[2];
   __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_rs[2];
+  __shared__ double s_nextp[kMaxClasses];   // next row of probabilities, fetched with cp.async (f32 rows use the first half)   // "a node was revived" flags of the last two commits
   __shared__ uint32_t s_cnt[kCommitRounds * (NT / 32) + 1];
   __shared__ uint32_t s_warp[NT / 32 + 1];
   __shared__ float s_red[NT / 32];
@@ -453,6 +497,8 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   uint32_t* const aux_cm[2] = {aux_base + 2 * WC, aux_base + 3 * WC};
   // ---- load the live list left by the previous launch
   int cur = 0;
+  uint32_t rescan = 1, cpar = 0;  // see phase 0 / phase 6
+  if (tid == 0) { s_rs[0] = 0; s_rs[1] = 0; }
   for (uint32_t i = tid; i < n_live; i += NT) {
     LiveList<WC>& L = sm.live[0];
     const uint32_t nd = s.node[i];
@@ -479,6 +525,18 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   };
   auto prob_d = [&](int row, int c) -> double {
     return use64 ? in.probs64[(size_t)row * C + c] : (double)in.probs[(size_t)row * C + c];
+  };
+  // thread c < C waits for ITS element of the prefetched row and turns it into the class log-prob; the blank's thread
+  // also prepares the gate (:125) and log(blank) for min_cutoff (:143)
+  auto next_row_ready = [&](int buf) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const double pd = use64 ? s_nextp[tid] : (double)reinterpret_cast<const float*>(s_nextp)[tid];
+    const float pf = use64 ? (float)s_nextp[tid] : reinterpret_cast<const float*>(s_nextp)[tid];
+    s_logp2[buf][tid] = sttmath::glibc_logf(pf + kFltMin);
+    if (tid == blank) {
+      s_gate[buf] = pd < 0.999 ? 1u : 0u;
+      s_logblank[buf] = log(pd);
+    }
   };
   for (uint32_t i = tid; i < (uint32_t)WC; i += NT) sm.child[i] = 0;
   for (int h = tid; h < 256; h += NT) s_hist[h] = 0;
@@ -508,18 +566,37 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     //      into log-probs at the end of this step, off the critical path.
     const int cb = step & 1;
     const float* s_logp = s_logp2[cb];
-    float next_p = 0.f;
     const bool have_next = (step + 1 < in.n_steps);
-    if (have_next && tid < C) next_p = prob_f(step + 1, tid);
+    if (have_next && tid < C) {
+      // asynchronous copy straight into shared memory: a register destination would be spilled, and the spill store
+      // would wait out the DRAM latency right here
+      if (use64) {
+        const double* src = in.probs64 + (size_t)(step + 1) * C + tid;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_nextp[tid])), "l"(src) : "memory");
+      } else {
+        const float* src = in.probs + (size_t)(step + 1) * C + tid;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(reinterpret_cast<float*>(s_nextp) + tid)), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     if (start_expanding | s_gate[cb]) {
-      for (uint32_t j = tid; j < n_live; j += NT) {
-        const uint32_t pn = L.pnode[j];
-        uint32_t pi = kNone;
-        if (pn != kNone) {
-          pi = s.nodes[pn].live_slot;
+      if (rescan) {
+        // first expanding step of a launch, or a pruned node was revived by the last commit: ask the arena
+        for (uint32_t j = tid; j < n_live; j += NT) {
+          const uint32_t pn = L.pnode[j];
+          uint32_t pi = kNone;
+          if (pn != kNone) {
+            pi = s.nodes[pn].live_slot;
+            if (pi != kNone) atomicOr(&sm.child[pi], 1u << L.chr[j]);
+          }
+          sm.plive[j] = pi;
+        }
+      } else {
+        // the last commit left every prefix's parent slot in plive (old slot -> new slot map, phase 6)
+        for (uint32_t j = tid; j < n_live; j += NT) {
+          const uint32_t pi = sm.plive[j];
           if (pi != kNone) atomicOr(&sm.child[pi], 1u << L.chr[j]);
         }
-        sm.plive[j] = pi;
       }
     }
     {
@@ -534,14 +611,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     __syncthreads();
     PHASE_MARK(1);
     if (!start_expanding || overflow) {
-      if (have_next) {
-        if (tid < C) s_logp2[cb ^ 1][tid] = sttmath::glibc_logf(next_p + kFltMin);
-        if (tid == 0) {
-          const double pb = prob_d(step + 1, blank);
-          s_gate[cb ^ 1] = pb < 0.999 ? 1u : 0u;
-          s_logblank[cb ^ 1] = log(pb);
-        }
-      }
+      if (have_next && tid < C) next_row_ready(cb ^ 1);
       __syncthreads();
       continue;
     }
@@ -691,39 +761,58 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     }
     PHASE_MARK(3);
 
-    // ---- phase 4b: write the new children
-    for (uint32_t i = tid; i < n_live; i += NT) {
-      uint32_t allow = sm.child[i];
-      if (!allow) continue;
-      uint32_t e = n_live + sm.lmq[i];
-      const float si = L.score[i];
-      const float bp = L.b[i];
-      const uint32_t cp = (L.chr[i] == (uint8_t)kRootChar) ? kRootChar : (uint32_t)L.chr[i];
-      while (allow) {
-        const int c = __ffs(allow) - 1;
-        allow &= allow - 1;
+    // ---- phase 4b: write the new children.  A prefix with few children is expanded by its own thread; one with many
+    //      (a word start allows every letter) would keep the other 31 lanes of its warp waiting, so those are expanded
+    //      by the whole warp, one lane per label.
+    for (uint32_t base = 0; base < n_live; base += NT) {
+      const uint32_t i = base + tid;
+      const int lane = tid & 31;
+      uint32_t allow = (i < n_live) ? sm.child[i] : 0u;
+      float si = 0.f, bp = 0.f, lmt = 0.f;
+      uint32_t cp = kRootChar, e0 = 0;
+      if (allow) {
+        e0 = n_live + sm.lmq[i];
+        si = L.score[i];
+        bp = L.b[i];
+        cp = (L.chr[i] == (uint8_t)kRootChar) ? kRootChar : (uint32_t)L.chr[i];
+        if (p.has_scorer && ((allow >> p.space_id) & 1u)) lmt = sm.lmterm[i];
+      }
+      auto emit = [&](uint32_t ii, uint32_t e, int c, float s_i, float b_p, uint32_t c_p, float lm_t) {
         float lp;
-        if ((uint32_t)c == cp) lp = (bp > kNegMax) ? s_logp[c] + bp : kNegMax;
-        else lp = s_logp[c] + si;
+        if ((uint32_t)c == c_p) lp = (b_p > kNegMax) ? s_logp[c] + b_p : kNegMax;
+        else lp = s_logp[c] + s_i;
         if (p.has_scorer && c == p.space_id) {
-          lp += sm.lmterm[i];
+          lp += lm_t;
           lp = (float)((double)lp + sv.beta);
         }
         K[e] = make_key(lp, (uint32_t)c, e);
-        P0[e] = i | ((uint32_t)c << 16);   // the child's dictionary state is looked up in phase 6, for survivors only
-        ++e;
+        P0[e] = ii | ((uint32_t)c << 16);   // the child's dictionary state is looked up in phase 6, for survivors only
+      };
+      const bool heavy = __popc(allow) > 6;
+      uint32_t hv = __ballot_sync(0xffffffffu, heavy);
+      while (hv) {
+        const int src = __ffs(hv) - 1;
+        hv &= hv - 1;
+        const uint32_t a = __shfl_sync(0xffffffffu, allow, src);
+        const uint32_t eb = __shfl_sync(0xffffffffu, e0, src);
+        const float s_i = __shfl_sync(0xffffffffu, si, src), b_p = __shfl_sync(0xffffffffu, bp, src);
+        const float lm_t = __shfl_sync(0xffffffffu, lmt, src);
+        const uint32_t c_p = __shfl_sync(0xffffffffu, cp, src);
+        if ((a >> lane) & 1u) emit(base + (tid & ~31) + src, eb + __popc(a & ((1u << lane) - 1u)), lane, s_i, b_p, c_p, lm_t);
+      }
+      if (!heavy) {
+        uint32_t e = e0;
+        while (allow) {
+          const int c = __ffs(allow) - 1;
+          allow &= allow - 1;
+          emit(i, e, c, si, bp, cp, lmt);
+          ++e;
+        }
       }
     }
     __syncthreads();
     for (uint32_t i = tid; i < (uint32_t)WC; i += NT) sm.child[i] = 0;  // ready for the next step's phase 0
-    if (have_next) {
-      if (tid < C) s_logp2[cb ^ 1][tid] = sttmath::glibc_logf(next_p + kFltMin);
-      if (tid == NT - 1) {
-        const double pb = prob_d(step + 1, blank);
-        s_gate[cb ^ 1] = pb < 0.999 ? 1u : 0u;
-        s_logblank[cb ^ 1] = log(pb);
-      }
-    }
+    if (have_next && tid < C) next_row_ready(cb ^ 1);
     PHASE_MARK(4);
 
     // ---- phase 5: exact top-W radix select on the 64-bit key (:263-274 nth_element + prefix_compare)
@@ -786,7 +875,6 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     //     candidates share ONE scan: per-round warp ballots, a 128-entry scan of the warp counts by warp 0.
     uint32_t out_base = 0;
     for (uint32_t g0 = 0; g0 < N; g0 += kCommitRounds * NT) {
-      unsigned long long keyq[kCommitRounds];
       uint32_t bal[kCommitRounds];
       const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -798,7 +886,6 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           key = K[e];
           keep = (N <= (uint32_t)W) || ((key & sel_mask) >= sel_prefix);
         }
-        keyq[q] = key;
         bal[q] = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_cnt[q * (NT / 32) + warp] = __popc(bal[q]);
       }
@@ -826,7 +913,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         if (e >= N) break;
         const bool keep = (bal[q] >> lane) & 1u;
         const uint32_t pos = out_base + s_cnt[q * (NT / 32) + warp] + __popc(bal[q] & ((1u << lane) - 1u));
-        const unsigned long long key = keyq[q];
+        const unsigned long long key = K[e];
         if (e < n_live) {
           const uint32_t nd = L.node[e];
           if (keep) {
@@ -851,11 +938,11 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
               Nx.ts[pos] = L.ts[e];
             }
             s.nodes[nd].live_slot = pos;
-            sm.lmq[pos] = kNone;  // not a new node
-            sm.plive[e] = pos;    // old live index -> new live index, for the children created below
+            sm.lmq[pos] = 0x80000000u | e;  // not a new node: remember the old slot
+            sm.tsprev[e] = pos;             // tsprev now maps old live slot -> new live slot (kNone = pruned)
           } else {
             s.nodes[nd].live_slot = kNone;
-            sm.plive[e] = kNone;
+            sm.tsprev[e] = kNone;
           }
         } else if (keep) {
           const float lp = unsortable((uint32_t)(key >> 32));
@@ -869,71 +956,94 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       __syncthreads();
     }
     PHASE_MARK(7);
-    // (ii) one thread per NEW survivor does the global-memory work (dictionary arc / child lookup / arena node / FST
-    //      state / timestep node), so all those latencies overlap instead of being paid once per 512-candidate round.
-    //      Lookups of previously created children (rare) finish before any list is modified.
-    for (uint32_t base = 0; base < out_base; base += NT) {
-      const uint32_t pos = base + tid;
-      const uint32_t pk = (pos < out_base) ? sm.lmq[pos] : kNone;
-      const bool active = (pk != kNone);
+    // (ii) one thread per survivor.  A NEW survivor does the global-memory work (dictionary arc / arena node / child-list
+    //      push / timestep node), all latencies overlapping; every survivor also works out where its parent sits in
+    //      the next live list, which saves phase 0 a round trip to the arena.
+    uint32_t my_plive[(WC + NT - 1) / NT];
+    uint2* const rev = reinterpret_cast<uint2*>(sm.lmterm);   // lmterm is dead until the next LM phase
+    constexpr int kRevCap = WC / 2;
+#pragma unroll
+    for (int r = 0; r < (WC + NT - 1) / NT; ++r) {
+      const uint32_t pos = (uint32_t)r * NT + tid;
+      my_plive[r] = kNone;
+      if (pos >= out_base) continue;
+      const uint32_t pk = sm.lmq[pos];
+      if (pk & 0x80000000u) {
+        const uint32_t po = sm.plive[pk & 0xffffu];
+        if (po != kNone) my_plive[r] = sm.tsprev[po];
+        continue;
+      }
       const uint32_t pi = pk & 0xffffu, c = (pk >> 16) & 0xffu;
-      uint32_t id = kNone, pnode = kNone, cord = 0, own_mask = 0;
-      int32_t nds = 0;
-      uint2 st = make_uint2(0u, all_labels);
       const bool is_space = ((int)c == p.space_id);
-      if (active) {
-        pnode = L.node[pi];
-        if (p.has_scorer) {
-          const uint32_t ai = L.pos[pi] + __popc(L.mask[pi] & ((1u << c) - 1u));
-          nds = __ldg(&p.fst_arc2[ai]).y;
-          if (p.fst_arc_skip && !is_space) cord = ordL[pi] + __ldg(p.fst_arc_skip + ai);
-          st = __ldg(&p.fst_state2[nds]);
-        }
-        if ((cmL[pi] >> c) & 1u) {
-          id = child_find(s, pnode, c);
-          if (id != kNone) own_mask = s.nodes[id].child_mask;
+      const uint32_t pnode = L.node[pi];
+      const uint32_t np = sm.tsprev[pi];   // the parent's slot in the next live list, if it survived
+      my_plive[r] = np;
+      int4 arc = make_int4(0, 0, (int)all_labels, 0);
+      if (p.has_scorer) arc = __ldg(&p.fst_arc4[L.pos[pi] + __popc(L.mask[pi] & ((1u << c) - 1u))]);
+      uint32_t id = kNone, own_mask = 0;
+      if ((cmL[pi] >> c) & 1u) {  // this child existed before (rare): find it, it is revived under its old identity
+        id = ht_find_existing(s, pnode, c);
+        own_mask = *reinterpret_cast<volatile uint32_t*>(&s.nodes[id].child_mask);
+        s.nodes[id].live_slot = pos;
+        const uint32_t ri = atomicAdd(&s_rs[cpar], 1u);   // tell the live children of this node where it sits now
+        if (ri < (uint32_t)kRevCap) rev[ri] = make_uint2(id, pos);
+      }
+      const uint32_t cord = (is_space || !p.fst_space_skip) ? 0u : ordL[pi] + (uint32_t)arc.w;
+      const float lp = Nx.score[pos];
+      if (id == kNone) {
+        id = atomicAdd(&s_u[5], 1u);  // fresh arena node
+        if (id < s.arena_cap) {
+          Node n;
+          n.parent = pnode; n.chr = c; n.dict = arc.x; n.last_space = is_space ? id : L.lsp[pi];
+          n.word_id = is_space ? (p.has_scorer ? sm.lmwid[pi] : 0u) : cord;
+          n.live_slot = pos; n.lm_wid = kNone; n.child_mask = 0;
+          s.nodes[id] = n;
+          s.lm_meta[id] = kNone;  // LM cache of this node: not computed
+          ht_insert(s, pnode, c, id);
+          atomicOr(&s.nodes[pnode].child_mask, 1u << c);
+          if (np != kNone) atomicOr(&cmN[np], 1u << c);
         }
       }
-      __syncthreads();
-      if (active) {
-        const float lp = Nx.score[pos];
-        if (id == kNone) {
-          id = atomicAdd(&s_u[5], 1u);  // fresh arena node
-          if (id < s.arena_cap) {
-            const uint32_t old_head = atomicExch(&s.links[pnode].x, id);
-            atomicOr(&s.nodes[pnode].child_mask, 1u << c);
-            Node n;
-            n.parent = pnode; n.chr = c; n.dict = nds; n.last_space = is_space ? id : L.lsp[pi];
-            n.word_id = is_space ? (p.has_scorer ? sm.lmwid[pi] : 0u) : cord;
-            n.live_slot = pos; n.lm_wid = kNone; n.child_mask = 0;
-            s.nodes[id] = n;
-            const uint32_t np = sm.plive[pi];   // the parent's slot in the next live list, if it survived
-            if (np != kNone) atomicOr(&cmN[np], 1u << c);
-            s.links[id] = make_uint2(kNone, old_head);
-          }
-        } else {
-          s.nodes[id].live_slot = pos;  // revived under its old identity
-        }
-        Nx.node[pos] = id;
-        Nx.pnode[pos] = pnode;
-        Nx.lsp[pos] = is_space ? id : L.lsp[pi];
-        Nx.chr[pos] = (uint8_t)c;
-        Nx.dict[pos] = nds;
-        ordN[pos] = cord;    // 0 for a space node: the next word starts here
-        cmN[pos] = own_mask;
-        Nx.pos[pos] = st.x;
-        Nx.mask[pos] = st.y;
-        if (lp > kNegMax) {  // "prefix_new->log_prob_nb_cur < log_p" (:246-251)
-          const uint32_t tid2 = ts_count + pos;
-          if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L.ts[pi]; s.ts_val[tid2] = abs_t; }
-          Nx.ts[pos] = tid2;
-        } else {
-          Nx.ts[pos] = kNone;
-        }
+      Nx.node[pos] = id;
+      Nx.pnode[pos] = pnode;
+      Nx.lsp[pos] = is_space ? id : L.lsp[pi];
+      Nx.chr[pos] = (uint8_t)c;
+      Nx.dict[pos] = arc.x;
+      Nx.pos[pos] = (uint32_t)arc.y;
+      Nx.mask[pos] = (uint32_t)arc.z;
+      ordN[pos] = cord;    // 0 for a space node: the next word starts here
+      cmN[pos] = own_mask;
+      if (lp > kNegMax) {  // "prefix_new->log_prob_nb_cur < log_p" (:246-251)
+        const uint32_t tid2 = ts_count + pos;
+        if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L.ts[pi]; s.ts_val[tid2] = abs_t; }
+        Nx.ts[pos] = tid2;
+      } else {
+        Nx.ts[pos] = kNone;
       }
     }
-    const uint32_t n_surv = out_base;
     __syncthreads();
+    {
+      // prefixes whose parent was not live may have just got it back: revived nodes announce their new slot
+      const uint32_t n_rev = s_rs[cpar];
+      rescan = n_rev > (uint32_t)kRevCap ? 1u : 0u;
+#pragma unroll
+      for (int r = 0; r < (WC + NT - 1) / NT; ++r) {
+        const uint32_t pos = (uint32_t)r * NT + tid;
+        if (pos >= out_base) continue;
+        uint32_t pl = my_plive[r];
+        if (pl == kNone && n_rev != 0 && !rescan && (sm.lmq[pos] & 0x80000000u)) {
+          const uint32_t pn = Nx.pnode[pos];
+          for (uint32_t k = 0; k < n_rev; ++k) {
+            const uint2 rv = rev[k];
+            if (rv.x == pn) pl = rv.y;
+          }
+        }
+        sm.plive[pos] = pl;
+      }
+      cpar ^= 1;
+      if (tid == 0) s_rs[cpar] = 0;
+    }
+    const uint32_t n_surv = out_base;
     arena_count = s_u[5];
     ts_count += n_surv;
     if (arena_count > s.arena_cap || ts_count > s.ts_cap) overflow = 1;

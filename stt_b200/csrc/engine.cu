@@ -143,9 +143,8 @@ struct Engine {
   uint8_t* scorer_blob = nullptr;
   sttscorer::ScorerView scorer_view{};
   uint2* fst_state2 = nullptr;  // per state {first arc, label mask}
-  int2* fst_arc2 = nullptr;     // per arc {ilabel, child dictionary state}
-  uint32_t* fst_arc_skip = nullptr;    // word-ordinal tables (decoder.cuh DecodeParams), null when not applicable
-  uint32_t* fst_space_skip = nullptr;
+  int4* fst_arc4 = nullptr;     // per arc {child dictionary state, its first arc, its label mask, word-ordinal skip}
+  uint32_t* fst_space_skip = nullptr;  // word-ordinal tables (decoder.cuh DecodeParams), null when not applicable
   uint32_t* ord2wid = nullptr;
 };
 
@@ -330,14 +329,13 @@ Engine* engine_create(const sttmodel::HostModel& m, std::string* err) {
 void engine_clear_scorer(Engine* e) {
   if (e->scorer_blob) cudaFree(e->scorer_blob);
   if (e->fst_state2) cudaFree(e->fst_state2);
-  if (e->fst_arc2) cudaFree(e->fst_arc2);
-  if (e->fst_arc_skip) cudaFree(e->fst_arc_skip);
+  if (e->fst_arc4) cudaFree(e->fst_arc4);
   if (e->fst_space_skip) cudaFree(e->fst_space_skip);
   if (e->ord2wid) cudaFree(e->ord2wid);
-  e->fst_arc_skip = e->fst_space_skip = e->ord2wid = nullptr;
+  e->fst_space_skip = e->ord2wid = nullptr;
   e->scorer_blob = nullptr;
   e->fst_state2 = nullptr;
-  e->fst_arc2 = nullptr;
+  e->fst_arc4 = nullptr;
   e->has_scorer = false;
 }
 
@@ -358,7 +356,7 @@ void engine_destroy(Engine* e) {
 // arc_skip along a word's arcs is its rank among the FST's words in label order.  ord2wid maps that rank to the KenLM
 // vocabulary id of the word's bytes (the same vocab_index the walking path calls).  Anything unexpected -- a cycle, a
 // word that does not end with the space label, more than 2^31 words -- leaves the tables null (walking path).
-void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_t* bytes) {
+void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_t* bytes, std::vector<uint32_t>* skip_out) {
   const int64_t nS = v.fst_nstates, nA = v.fst_narcs;
   if (nS <= 0 || nA <= 0 || v.fst_start < 0 || v.fst_start >= nS) return;
   struct Arc { int32_t il, nx; };
@@ -449,19 +447,17 @@ void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_
     }
   }
   if (seen != n_words) return;
-  if (cudaMalloc(reinterpret_cast<void**>(&e->fst_arc_skip), skip.size() * 4) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&e->fst_space_skip), space_skip.size() * 4) != cudaSuccess ||
+  if (cudaMalloc(reinterpret_cast<void**>(&e->fst_space_skip), space_skip.size() * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&e->ord2wid), o2w.size() * 4) != cudaSuccess) {
     cudaGetLastError();
-    if (e->fst_arc_skip) cudaFree(e->fst_arc_skip);
     if (e->fst_space_skip) cudaFree(e->fst_space_skip);
     if (e->ord2wid) cudaFree(e->ord2wid);
-    e->fst_arc_skip = e->fst_space_skip = e->ord2wid = nullptr;
+    e->fst_space_skip = e->ord2wid = nullptr;
     return;
   }
-  cudaMemcpy(e->fst_arc_skip, skip.data(), skip.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(e->fst_space_skip, space_skip.data(), space_skip.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(e->ord2wid, o2w.data(), o2w.size() * 4, cudaMemcpyHostToDevice);
+  *skip_out = std::move(skip);
   if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] dictionary word ordinals: %llu words\n", (unsigned long long)n_words);
 }
 
@@ -501,17 +497,24 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
           memcpy(&prev, arc - 16, 4);
           if (prev >= il) return sttscorer::SCORER_INVALID_TRIE;  // SortedMatcher needs ilabel-sorted, deterministic arcs
         }
+        if (nx < 0 || nx >= v.fst_nstates || (uint64_t)pos + a >= (uint64_t)v.fst_narcs) return sttscorer::SCORER_INVALID_TRIE;
         const bool fin = sttscorer::fst_is_final(v, nx);
         ar2[pos + a] = make_int2(il, fin ? (int32_t)v.fst_start : nx);
       }
       st2[(size_t)q] = make_uint2(pos, mask);
     }
+    std::vector<uint32_t> skip;
+    build_word_ordinals(e, v, bytes, &skip);
+    std::vector<int4> ar4(ar2.size());
+    for (size_t i = 0; i < ar2.size(); ++i) {
+      const uint2 cs = st2[(size_t)ar2[i].y];
+      ar4[i] = make_int4(ar2[i].y, (int)cs.x, (int)cs.y, skip.empty() ? 0 : (int)skip[i]);
+    }
     if (cudaMalloc(reinterpret_cast<void**>(&e->fst_state2), std::max<size_t>(st2.size(), 1) * sizeof(uint2)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&e->fst_arc2), std::max<size_t>(ar2.size(), 1) * sizeof(int2)) != cudaSuccess)
+        cudaMalloc(reinterpret_cast<void**>(&e->fst_arc4), std::max<size_t>(ar4.size(), 1) * sizeof(int4)) != cudaSuccess)
       return sttscorer::SCORER_UNREADABLE;
     cudaMemcpy(e->fst_state2, st2.data(), st2.size() * sizeof(uint2), cudaMemcpyHostToDevice);
-    cudaMemcpy(e->fst_arc2, ar2.data(), ar2.size() * sizeof(int2), cudaMemcpyHostToDevice);
-    build_word_ordinals(e, v, bytes);
+    cudaMemcpy(e->fst_arc4, ar4.data(), ar4.size() * sizeof(int4), cudaMemcpyHostToDevice);
   }
   v.blob = e->scorer_blob;
   e->scorer_view = v;
@@ -524,6 +527,7 @@ struct Batch {
   Engine* e = nullptr;
   int B_cap = 0, S_cap = 0, T_cap = 0, beam_cap = 0, dec_T_cap = 0, max_results = 0;
   int B = 0, T_max = 0;
+  uint32_t ht_gen = 0;  // generation of the decoder hash tables (decoder_reset)
   std::vector<int> T;  // timesteps per utterance
   cudaStream_t st = nullptr;
   cudaEvent_t ev[12];
@@ -594,7 +598,10 @@ int alloc_slots(Batch* b) {
   };
   const int SW = sttdec::kStateWords;
   const size_t o_nodes = take(sizeof(sttdec::Node) * (size_t)arena_cap);
-  const size_t o_links = take(sizeof(uint2) * (size_t)arena_cap);
+  if (arena_cap >= (1u << 24)) return -1;  // hash entries hold 24-bit node ids
+  uint32_t ht = 1;
+  while (ht < 2u * arena_cap) ht <<= 1;
+  const size_t o_ht = take(8ull * ht);
   const size_t o_lmc = take(8ull * arena_cap), o_lmsw = take(4ull * arena_cap * SW), o_lmsb = take(4ull * arena_cap * SW);
   const size_t o_lmm = take(4ull * arena_cap);
   const size_t o_tsp = take(4ull * ts_cap), o_tsv = take(4ull * ts_cap);
@@ -603,12 +610,15 @@ int alloc_slots(Batch* b) {
   const size_t o_scal = take(64), o_ph = take(64), o_aux = take(W > 512 ? 16ull * 2048 : 256);  // StepSmem::aux of the wide instantiation (WC = 2048)
   b->slot_bytes = off;
   CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_slot_mem), b->slot_bytes * b->B_cap));
+  CUDA_OK(cudaMemset(b->d_slot_mem, 0, b->slot_bytes * b->B_cap));  // hash tables start at generation 0 = empty
   b->h_slots.resize(b->B_cap);
   for (int u = 0; u < b->B_cap; ++u) {
     uint8_t* base = b->d_slot_mem + b->slot_bytes * u;
     sttdec::Slot& s = b->h_slots[u];
     s.nodes = (sttdec::Node*)(base + o_nodes);
-    s.links = (uint2*)(base + o_links);
+    s.ht = (unsigned long long*)(base + o_ht);
+    s.ht_mask = ht - 1;
+    s.ht_gen = 0;
     s.lm_cond = (double*)(base + o_lmc); s.lm_sw = (uint32_t*)(base + o_lmsw); s.lm_sb = (float*)(base + o_lmsb);
     s.lm_meta = (uint32_t*)(base + o_lmm);
     s.ts_parent = (uint32_t*)(base + o_tsp); s.ts_val = (uint32_t*)(base + o_tsv);
@@ -1011,10 +1021,9 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
   dp.has_scorer = e->has_scorer ? 1 : 0;
   if (e->has_scorer) dp.scorer = e->scorer_view;
   dp.fst_state2 = e->fst_state2;
-  dp.fst_arc2 = e->fst_arc2;
-  dp.fst_arc_skip = getenv("STT_B200_NO_WORD_ORDINALS") ? nullptr : e->fst_arc_skip;
-  dp.fst_space_skip = dp.fst_arc_skip ? e->fst_space_skip : nullptr;
-  dp.ord2wid = dp.fst_arc_skip ? e->ord2wid : nullptr;
+  dp.fst_arc4 = e->fst_arc4;
+  dp.fst_space_skip = getenv("STT_B200_NO_WORD_ORDINALS") ? nullptr : e->fst_space_skip;
+  dp.ord2wid = dp.fst_space_skip ? e->ord2wid : nullptr;
   dp.n_hot = e->has_scorer ? (int)std::min<size_t>(b->hot_ids.size(), sttdec::kMaxHotWords) : 0;
   for (int h = 0; h < dp.n_hot; ++h) {
     dp.hot_id[h] = b->hot_ids[h];
@@ -1026,7 +1035,13 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
 int decoder_reset(Batch* b, int n_slots) {
   cudaStream_t st = b->st;
   const int32_t fst_start = b->e->has_scorer ? (int32_t)b->e->scorer_view.fst_start : 0;
-  sttdec::decoder_init_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b->d_slots, n_slots, fst_start);
+  // (parent, label) hash tables are never cleared between decodes: entries carry a generation (decoder.cuh ht_insert)
+  if (++b->ht_gen > 255u) {
+    for (int u = 0; u < b->B_cap; ++u)
+      CUDA_OK(cudaMemsetAsync(b->h_slots[u].ht, 0, 8ull * ((size_t)b->h_slots[u].ht_mask + 1), st));
+    b->ht_gen = 1;
+  }
+  sttdec::decoder_init_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b->d_slots, n_slots, fst_start, b->ht_gen);
   CUDA_OK(cudaGetLastError());
   b->launches += 1;
   return 0;

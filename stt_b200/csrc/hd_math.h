@@ -207,8 +207,11 @@ STT_HD float log_sum_exp(float x, float y) {
   const float num_min = -3.402823466e+38f;
   if (x <= num_min) return y;
   if (y <= num_min) return x;
-  float xmax = x > y ? x : y;  // std::max(x, y): returns x when equal
-  return glibc_logf(glibc_expf(x - xmax) + glibc_expf(y - xmax)) + xmax;
+  // std::max(x, y) returns x when equal.  One of the two exponents is exactly 0 and expf(0) == 1.0f exactly (the
+  // exhaustive libm check covers it), float addition commutes, so only the other expf is evaluated.
+  const float xmax = x > y ? x : y;
+  const float d = x > y ? y - xmax : x - xmax;
+  return glibc_logf(1.0f + glibc_expf(d)) + xmax;
 }
 
 }  // namespace sttmath
