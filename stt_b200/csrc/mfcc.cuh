@@ -2,7 +2,8 @@
 //
 // Restates, per window, the reference chain (all double precision internally, like the TFLite kernels):
 //   stt.cc:105-128                    int16 -> f32 (x 1/32768), 512-sample window, hop 320, zero-padded tail
-//   internal/spectrogram.cc:30-37     periodic Hann; :224-241 real FFT (any exact DFT agrees to ~1e-13);
+//   internal/spectrogram.cc:30-37     periodic Hann; :224-241 real FFT (any exact DFT agrees to ~1e-13; here three
+//                                     radix-8 passes with register butterflies);
 //                                     :175-183 re^2+im^2 in double, stored as float
 //   internal/mfcc_mel_filterbank.cc:172-197   sqrt, 40 triangular bands (tables built on the host exactly as
 //                                     :40-167 does, in the same accumulation order per channel)
@@ -57,46 +58,114 @@ __device__ __forceinline__ int n_frames_for(int n, int win_len, int win_step) {
 
 constexpr int kWarpsPerBlock = 4;
 
+// 512 complex points, padded by one element per 8 so that the radix-8 passes below store without bank conflicts.
+__device__ __forceinline__ int zidx(int i) { return i + (i >> 3); }
+
 struct WarpScratch {
-  double re[kFft];
-  double im[kFft];
+  double2 z[kFft + kFft / 8];   // FFT work array; afterwards its first kBins doubles hold sqrt(power)
   float pow[kBins + 3];
   double mel[kMaxChannels];
 };
 
-// One WARP per analysis window (v1 used one 256-thread CTA per window and spent its time in __syncthreads; a warp
-// needs only __syncwarp between FFT stages and 20 windows are in flight per SM instead of 8).
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// forward 8-point DFT in registers (decimation in frequency): a[] -> X[0..7] in natural order
+__device__ __forceinline__ void dft8(double2 (&a)[8]) {
+  const double c = 0.70710678118654752440;
+  double2 t0 = make_double2(a[0].x + a[4].x, a[0].y + a[4].y), t4 = make_double2(a[0].x - a[4].x, a[0].y - a[4].y);
+  double2 t1 = make_double2(a[1].x + a[5].x, a[1].y + a[5].y), t5 = make_double2(a[1].x - a[5].x, a[1].y - a[5].y);
+  double2 t2 = make_double2(a[2].x + a[6].x, a[2].y + a[6].y), t6 = make_double2(a[2].x - a[6].x, a[2].y - a[6].y);
+  double2 t3 = make_double2(a[3].x + a[7].x, a[3].y + a[7].y), t7 = make_double2(a[3].x - a[7].x, a[3].y - a[7].y);
+  // odd branch twiddles: w^1 = (1 - i)/sqrt2, w^2 = -i, w^3 = (-1 - i)/sqrt2
+  t5 = make_double2(c * (t5.x + t5.y), c * (t5.y - t5.x));
+  t6 = make_double2(t6.y, -t6.x);
+  t7 = make_double2(c * (t7.y - t7.x), -c * (t7.x + t7.y));
+  // two 4-point DFTs
+  auto dft4 = [](double2 b0, double2 b1, double2 b2, double2 b3, double2& y0, double2& y1, double2& y2, double2& y3) {
+    const double2 u0 = make_double2(b0.x + b2.x, b0.y + b2.y), u1 = make_double2(b0.x - b2.x, b0.y - b2.y);
+    const double2 u2 = make_double2(b1.x + b3.x, b1.y + b3.y);
+    const double2 d = make_double2(b1.x - b3.x, b1.y - b3.y);
+    const double2 u3 = make_double2(d.y, -d.x);  // (b1 - b3) * -i
+    y0 = make_double2(u0.x + u2.x, u0.y + u2.y);
+    y2 = make_double2(u0.x - u2.x, u0.y - u2.y);
+    y1 = make_double2(u1.x + u3.x, u1.y + u3.y);
+    y3 = make_double2(u1.x - u3.x, u1.y - u3.y);
+  };
+  dft4(t0, t1, t2, t3, a[0], a[2], a[4], a[6]);
+  dft4(t4, t5, t6, t7, a[1], a[3], a[5], a[7]);
+}
+// a[t] *= w1^t, t = 1..7
+__device__ __forceinline__ void twiddle8(double2 (&a)[8], double2 w1) {
+  const double2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+  const double2 w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w4, w3);
+  a[1] = cmul(a[1], w1); a[2] = cmul(a[2], w2); a[3] = cmul(a[3], w3); a[4] = cmul(a[4], w4);
+  a[5] = cmul(a[5], w5); a[6] = cmul(a[6], w6); a[7] = cmul(a[7], w7);
+}
+
+// One WARP per analysis window.  The 512-point DFT is three radix-8 Stockham passes with the butterflies in registers
+// (two per lane and pass); shared memory only carries the two transposes between passes -- 32 KB of traffic per
+// window where the radix-2 version moved 147 KB.  The input is real; the imaginary lanes cost ALU only, and fp64 ALU
+// is not what limits this kernel.
 __device__ __forceinline__ void mfcc_window(const MfccTables& tb, WarpScratch& w, const int16_t* pcm, int n_valid,
                                             float* out_f32, __half* out_f16) {
   const int lane = threadIdx.x & 31;
-  for (int j = lane; j < kFft; j += 32) {
-    double v = 0.0;
-    if (j < tb.win_len && j < n_valid) v = (double)((float)pcm[j] * (1.0f / 32768.0f)) * tb.hann[j];
-    const int r = __brev((unsigned)j) >> (32 - 9);
-    w.re[r] = v;
-    w.im[r] = 0.0;
+  double2 a[2][8];
+  // ---- pass 0 (Ns = 1): inputs x[j + 64 t], no twiddles, outputs at 8 j + t
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int n = j + 64 * t;
+      double v = 0.0;
+      if (n < tb.win_len && n < n_valid) v = (double)((float)pcm[n] * (1.0f / 32768.0f)) * tb.hann[n];
+      a[h][t] = make_double2(v, 0.0);
+    }
+    dft8(a[h]);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) w.z[zidx(8 * j + t)] = a[h][t];
   }
   __syncwarp();
-#pragma unroll 1
-  for (int len = 2; len <= kFft; len <<= 1) {
-    const int half = len >> 1;
-    const int tstep = kFft / len;
-#pragma unroll 4
-    for (int bf = lane; bf < kFft / 2; bf += 32) {
-      const int k = bf & (half - 1);
-      const int i = ((bf - k) << 1) + k;
-      const int j = i + half;
-      const double wr = tb.tw_re[k * tstep], wi = tb.tw_im[k * tstep];
-      const double xr = w.re[j] * wr - w.im[j] * wi, xi = w.re[j] * wi + w.im[j] * wr;
-      const double ur = w.re[i], ui = w.im[i];
-      w.re[j] = ur - xr;
-      w.im[j] = ui - xi;
-      w.re[i] = ur + xr;
-      w.im[i] = ui + xi;
-    }
-    __syncwarp();
+  // ---- pass 1 (Ns = 8): k = j mod 8, twiddle exp(-2 pi i t k / 64), outputs at (j / 8) * 64 + k + 8 t
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) a[h][t] = w.z[zidx(j + 64 * t)];
   }
-  for (int i = lane; i < kBins; i += 32) w.pow[i] = (float)(w.re[i] * w.re[i] + w.im[i] * w.im[i]);
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    const int k = j & 7;
+    twiddle8(a[h], make_double2(tb.tw_re[8 * k], tb.tw_im[8 * k]));
+    dft8(a[h]);
+    const int base = (j >> 3) * 64 + k;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) w.z[zidx(base + 8 * t)] = a[h][t];
+  }
+  __syncwarp();
+  // ---- pass 2 (Ns = 64): k = j, twiddle exp(-2 pi i t j / 512), output bin j + 64 t; only bins 0..256 are needed
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) a[h][t] = w.z[zidx(j + 64 * t)];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = lane + 32 * h;
+    twiddle8(a[h], make_double2(tb.tw_re[j], tb.tw_im[j]));
+    dft8(a[h]);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) w.pow[j + 64 * t] = (float)(a[h][t].x * a[h][t].x + a[h][t].y * a[h][t].y);
+    if (j == 0) w.pow[256] = (float)(a[h][4].x * a[h][4].x + a[h][4].y * a[h][4].y);
+  }
+  __syncwarp();
+  double* spec = reinterpret_cast<double*>(w.z);  // the work array is dead now
+  for (int i = lane; i < kBins; i += 32) spec[i] = sqrt((double)w.pow[i]);
   __syncwarp();
   for (int ch = lane; ch < tb.n_channels; ch += 32) {
     // same per-channel accumulation order as the reference's single pass over bins
@@ -104,7 +173,7 @@ __device__ __forceinline__ void mfcc_window(const MfccTables& tb, WarpScratch& w
     const int first = tb.chan_first_bin[ch], last = tb.chan_last_bin[ch];
     if (first >= 0) {
       for (int i = first; i <= last; ++i) {
-        const double spec_val = sqrt((double)w.pow[i]);
+        const double spec_val = spec[i];
         const double weighted = spec_val * tb.weights[i];
         const int m = tb.band_mapper[i];
         if (m == ch) acc += weighted;
