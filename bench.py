@@ -128,6 +128,17 @@ def cpu_sample(cp, pcms, seconds):
 
 
 # ------------------------------------------------------------------------------------------------ main
+def ncu_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel, from the committed ncu --set full
+    capture (profiles/traffic.json names the .md summary it was taken from); None when no capture exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(stage)
+        return float(t["dram_bytes_per_launch"]) if t else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -278,10 +289,10 @@ def main():
     dominant = max(roof_all, key=lambda k: roof_all[k]["ms"])
     roofline = dict(roof_all[dominant])
     roofline.update({"kernel": {"dense123": "gemm_tc_kernel<256,clip-relu> x3", "lstm_in": "gemm_tc_kernel<256,bias-f32>",
-                                "lstm": "lstm_tc_kernel", "dense56": "gemm_tc_kernel<256>+<32,softmax>",
+                                "lstm": "lstm_pp_kernel", "dense56": "gemm_tc_kernel<256>+<32,softmax>",
                                 "decode": "decoder_step_kernel"}[dominant],
                      "peak_source": which + (" (sustained bf16 cuBLAS)" if roof_all[dominant]["bound"] == "tensor" else " (copy)"),
-                     "traffic": None})
+                     "traffic": ncu_traffic(dominant)})
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": max(1, args.gpus), "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

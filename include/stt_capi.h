@@ -185,6 +185,8 @@ STT_EXPORT int STTX_BatchCopyProbs(STTX_Batch* b, unsigned int u, float* out);  
 STT_EXPORT int STTX_BatchSetProbs(STTX_Batch* b, const float* probs, const int* T, unsigned int n, unsigned int T_stride);
 /* decoder-only entry (the reference's Python ctc_beam_search_decoder_batch takes f64 probabilities) */
 STT_EXPORT int STTX_BatchSetProbs64(STTX_Batch* b, const double* probs, const int* T, unsigned int n, unsigned int T_stride);
+/* bring-up: TMEM layout of a CTA-pair MMA (M = 128 or 256); out = float[2][128][128] */
+STT_EXPORT int STTX_DebugPairLayout(int M, float* out);
 STT_EXPORT int STTX_DebugGemm(int M, int N, int K, const unsigned short* a_f16, const unsigned short* w_f16,
                               const float* bias, int epilogue, float relu_clip, void* out, float* ms);
 STT_EXPORT int STTX_ModelInfo(const ModelState* aCtx, unsigned int* n_classes, unsigned int* n_input, unsigned int* n_hidden,

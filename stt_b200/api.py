@@ -55,7 +55,7 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout",
 ]
 
 
@@ -134,6 +134,7 @@ def lib():
     L.STTX_BatchCopyProbs.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchSetProbs.argtypes = [vp, c_void_p, c_void_p, c_uint, c_uint]
     L.STTX_BatchSetProbs64.argtypes = [vp, c_void_p, c_void_p, c_uint, c_uint]
+    L.STTX_DebugPairLayout.argtypes = [c_int, c_void_p]
     L.STTX_DebugGemm.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                  POINTER(c_float)]
     L.STTX_ModelInfo.argtypes = [vp] + [POINTER(c_uint)] * 5

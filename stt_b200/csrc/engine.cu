@@ -15,6 +15,7 @@
 #include "decoder.cuh"
 #include "gemm_tc.cuh"
 #include "lstm2_tc.cuh"
+#include "probe_tc.cuh"
 #include "lstm_tc.cuh"
 #include "mfcc.cuh"
 #include "scorer_image.h"
@@ -694,7 +695,7 @@ Batch* batch_create(Engine* e, int B_cap, int max_samples, int beam_cap, int dec
   ok &= cudaMalloc((void**)&b->d_hall, (M_cap + B_cap + 256) * Cp * 2) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_c, (size_t)B_cap * Cp * 4) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_h, (size_t)B_cap * Cp * 4) == cudaSuccess;
-  ok &= cudaMalloc((void**)&b->d_barrier, 64) == cudaSuccess;
+  ok &= cudaMalloc((void**)&b->d_barrier, 16384) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_lstm_prof, 8 * 4 * 1024) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_probs, (size_t)B_cap * b->T_cap * C * 4) == cudaSuccess;
   ok &= cudaMalloc((void**)&b->d_win, (size_t)(b->T_cap + 1) * m.win_len * 2) == cudaSuccess;
@@ -888,9 +889,63 @@ int launch_lstm_pair(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStre
   return 0;
 }
 
+// Ping-pong CTA-pair kernel (two groups of <= 128 utterances, M = 128 MMAs); returns 1 if it cannot be used.
+template <int KB, int STAGES>
+int launch_lstm_pp_inst(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st) {
+  static int usable = -1;  // -1 unknown, 0 no, 1 yes
+  using L = sttlstm::PPSmem<KB, STAGES>;
+  auto kern = sttlstm::lstm_pp_kernel<KB, STAGES>;
+  cudaLaunchConfig_t cfgl{};
+  cfgl.gridDim = dim3(grid);
+  cfgl.blockDim = dim3(sttlstm::kPPThreads);
+  cfgl.dynamicSmemBytes = L::kTotal;
+  cfgl.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = 2;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfgl.attrs = attrs;
+  cfgl.numAttrs = 2;
+  if (usable < 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) { cudaGetLastError(); usable = 0; return 1; }
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfgl) != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
+    usable = (n_clusters * 2 >= grid) ? 1 : 0;
+    if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] LSTM ping-pong kernel<%d,%d>: %d co-resident pairs, usable=%d\n", KB, STAGES, n_clusters, usable);
+  }
+  if (!usable) return 1;
+  // 3-D views {64 columns, rows, K block}: one request brings KB K blocks of 64 rows
+  const int Cp = b->e->Cp;
+  CUtensorMap tm_h, tm_w;
+  {
+    const uint64_t rows = (uint64_t)b->T_cap * b->B_cap + b->B_cap + 256;
+    uint64_t dims[3] = {64, rows, (uint64_t)(Cp / 64)};
+    uint64_t strides[2] = {(uint64_t)Cp * 2, 128};
+    uint32_t box[3] = {64, 64, (uint32_t)KB};
+    if (!make_tmap(&tm_h, b->d_hall, 3, dims, strides, box)) return 1;
+    dims[1] = (uint64_t)4 * Cp;
+    if (!make_tmap(&tm_w, b->e->wh, 3, dims, strides, box)) return 1;
+  }
+  CUDA_OK(cudaLaunchKernelEx(&cfgl, kern, tm_h, tm_w, lp));
+  return 0;
+}
+int launch_lstm_pp(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st) {
+  static const char* env = getenv("STT_B200_LSTM_PINGPONG");
+  const int mode = env ? atoi(env) : 4;
+  if (mode == 0 || grid % 2 != 0) return 1;
+  if (mode == 2) return launch_lstm_pp_inst<2, 6>(b, lp, grid, st);
+  if (mode == 1) return launch_lstm_pp_inst<1, 12>(b, lp, grid, st);
+  return launch_lstm_pp_inst<4, 3>(b, lp, grid, st);
+}
+
 int launch_lstm(Batch* b, const sttlstm::LstmParams& lp, int grid, int B, cudaStream_t st) {
   if (B <= 128) return launch_lstm_mt<1, 6>(b, lp, grid, st);
-  const int rc = launch_lstm_pair(b, lp, grid, st);
+  int rc = launch_lstm_pp(b, lp, grid, st);
+  if (rc <= 0) return rc;
+  rc = launch_lstm_pair(b, lp, grid, st);
   if (rc <= 0) return rc;
   return launch_lstm_mt<2, 5>(b, lp, grid, st);
 }
@@ -948,7 +1003,7 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
   if (time_it) cudaEventRecord(b->ev[5], st);
   // ---- recurrence
   {
-    CUDA_OK(cudaMemsetAsync(b->d_barrier, 0, 4, st));
+    CUDA_OK(cudaMemsetAsync(b->d_barrier, 0, 16384, st));
     sttlstm::LstmParams lp{};
     lp.B = B; lp.T = T; lp.n_cell = Cp; lp.xw = b->d_xw; lp.h_all = b->d_hall; lp.c_state = b->d_c; lp.h_state = b->d_h;
     lp.barrier = b->d_barrier;
@@ -1222,6 +1277,15 @@ int batch_lstm_profile(Batch* b, unsigned long long* out3) {
   out3[0] = out3[1] = out3[2] = 0;
   for (int g = 0; g < grid; ++g)
     for (int k = 0; k < 3; ++k) out3[k] = std::max(out3[k], h[(size_t)g * 4 + k]);
+  if (getenv("STT_B200_VERBOSE")) {  // ping-pong kernel's extra role counters (cycles per launch, max over CTAs)
+    std::vector<unsigned long long> x((size_t)grid * 4);
+    cudaMemcpy(x.data(), b->d_lstm_prof + 2048, x.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long mx[4] = {0, 0, 0, 0};
+    for (int g = 0; g < grid; ++g)
+      for (int k = 0; k < 4; ++k) mx[k] = std::max(mx[k], x[(size_t)g * 4 + k]);
+    fprintf(stderr, "[stt_b200] lstm_pp roles: producer pre-phase %llu, producer main loop %llu, MMA wait for first tile %llu, epilogue wait for MMA %llu\n",
+            mx[0], mx[1], mx[2], mx[3]);
+  }
   return 0;
 }
 
@@ -1450,6 +1514,38 @@ int debug_gemm(int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16
   cudaEventDestroy(e1);
   cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dO);
   return rc;
+}
+
+// Bring-up helper: TMEM layout of a cta_group::2 MMA with the given M (128 or 256); out = [2 CTAs][128 lanes][128 cols].
+int debug_pair_layout(int M, float* out) {
+  if (M != 128 && M != 256) return -2;
+  std::vector<__half> ha((size_t)256 * 64, __float2half(0.f)), hb((size_t)128 * 64, __float2half(0.f));
+  for (int i = 0; i < 256; ++i) { ha[(size_t)i * 64 + 0] = __float2half((float)(i + 1)); ha[(size_t)i * 64 + 1] = __float2half(1.f); }
+  for (int n = 0; n < 128; ++n) { hb[(size_t)n * 64 + 0] = __float2half(1024.f); hb[(size_t)n * 64 + 1] = __float2half((float)(n + 1)); }
+  __half *dA, *dB;
+  float* dO;
+  CUDA_OK(cudaMalloc((void**)&dA, ha.size() * 2));
+  CUDA_OK(cudaMalloc((void**)&dB, hb.size() * 2));
+  CUDA_OK(cudaMalloc((void**)&dO, 2 * 128 * 128 * 4));
+  CUDA_OK(cudaMemset(dO, 0xff, 2 * 128 * 128 * 4));
+  CUDA_OK(cudaMemcpy(dA, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dB, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+  CUtensorMap ta, tb;
+  if (!make_tmap_2d(&ta, dA, 256, 64, 64, M / 2) || !make_tmap_2d(&tb, dB, 128, 64, 64, 64)) return -1;
+  auto kern = sttprobe::probe_pair_kernel;
+  const int smem = 16384 + 8192 + 64 + 1024;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, dO));
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(out, dO, 2 * 128 * 128 * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dO);
+  return 0;
 }
 
 }  // namespace stteng

@@ -65,6 +65,7 @@ int batch_stream_frames(const Batch* b);
 int batch_stream_last_probs(Batch* b, std::vector<double>* out, int* n_rows);
 
 // raw GEMM hook for the kernel unit tests: C = epi(A[M,K] * W[N,K]^T + bias)
+int debug_pair_layout(int M, float* out);
 int debug_gemm(int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16, const float* bias, int epi,
                float relu_clip, void* out, float* ms);
 
