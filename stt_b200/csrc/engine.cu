@@ -463,6 +463,7 @@ void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_
 }
 
 int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
+  cudaSetDevice(e->device);  // CUDA's current device is per host thread
   sttscorer::AlphabetBytes ab;
   ab.labels = e->hm.labels;
   ab.space_label = e->hm.space_label;
@@ -661,6 +662,7 @@ int alloc_slots(Batch* b) {
 }  // namespace
 
 Batch* batch_create(Engine* e, int B_cap, int max_samples, int beam_cap, int dec_T_cap, std::string* err) {
+  cudaSetDevice(e->device);  // CUDA's current device is per host thread
   const auto& m = e->hm;
   Batch* b = new Batch();
   b->e = e;
@@ -715,6 +717,7 @@ Batch* batch_create(Engine* e, int B_cap, int max_samples, int beam_cap, int dec
 
 void batch_destroy(Batch* b) {
   if (!b) return;
+  cudaSetDevice(b->e->device);
   if (b->st) cudaStreamSynchronize(b->st);
   for (void* p : {(void*)b->d_pcm, (void*)b->d_nsamples, (void*)b->d_feat, (void*)b->d_feat32, (void*)b->d_act_a,
                   (void*)b->d_act_b, (void*)b->d_xw, (void*)b->d_hall, (void*)b->d_c, (void*)b->d_h, (void*)b->d_barrier, (void*)b->d_lstm_prof, (void*)b->d_probs64,
@@ -736,6 +739,7 @@ int16_t* batch_host_pcm(Batch* b, int utt) {
 }
 
 int batch_upload(Batch* b, const int16_t* const* pcm, const unsigned* n_samples, int B) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (B < 1 || B > b->B_cap) return -1;
   const auto& m = b->e->hm;
   b->B = B;
@@ -1029,6 +1033,7 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
 }  // namespace
 
 int batch_forward(Batch* b) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   Engine* e = b->e;
   b->use_probs64 = false;
   const auto& m = e->hm;
@@ -1193,6 +1198,7 @@ void parse_results(const Batch* b, const uint8_t* base, std::vector<Decoded>* ou
 }  // namespace
 
 int batch_set_hot_words(Batch* b, const std::vector<std::string>& words, const std::vector<float>& boosts) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   // Words outside the LM vocabulary can never equal a word of a scored n-gram (every scored word passed the
   // dictionary, whose words come from the LM vocabulary), so they are dropped here.
   b->hot_ids.clear();
@@ -1219,6 +1225,7 @@ int batch_set_hot_words(Batch* b, const std::vector<std::string>& words, const s
 }
 
 int batch_decode(Batch* b, int beam, int num_results) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (b->B < 1 || beam < 1 || beam > b->beam_cap) return -1;
   if (ensure_results_capacity(b, num_results)) return -1;
   b->cur_beam = beam;
@@ -1241,6 +1248,7 @@ int batch_decode(Batch* b, int beam, int num_results) {
 }
 
 int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   cudaStream_t st = b->st;
   cudaEventRecord(b->ev[10], st);
   // header + first result rows are small; copy only what the results can occupy: [0, o_ts + used)
@@ -1261,6 +1269,7 @@ int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out) {
 }
 
 int batch_phase_cycles(Batch* b, unsigned long long* out8) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   for (int q = 0; q < 8; ++q) out8[q] = 0;
   for (int u = 0; u < b->B; ++u) {
     unsigned long long ph[8];
@@ -1271,6 +1280,7 @@ int batch_phase_cycles(Batch* b, unsigned long long* out8) {
 }
 
 int batch_lstm_profile(Batch* b, unsigned long long* out3) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   const int grid = b->e->Cp / sttlstm::kCellsPerCta;
   std::vector<unsigned long long> h((size_t)grid * 4);
   CUDA_OK(cudaMemcpy(h.data(), b->d_lstm_prof, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -1290,6 +1300,7 @@ int batch_lstm_profile(Batch* b, unsigned long long* out3) {
 }
 
 int batch_lm_stats(Batch* b, unsigned long long* words, unsigned long long* calls) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   *words = 0;
   *calls = 0;
   for (int u = 0; u < b->B; ++u) {
@@ -1302,18 +1313,21 @@ int batch_lm_stats(Batch* b, unsigned long long* words, unsigned long long* call
 }
 
 int batch_copy_features(Batch* b, int utt, float* out) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (utt < 0 || utt >= b->B) return -1;
   const int ni = b->e->hm.n_input;
   CUDA_OK(cudaMemcpy(out, b->d_feat32 + (size_t)utt * b->T_cap * ni, (size_t)b->T[utt] * ni * 4, cudaMemcpyDeviceToHost));
   return b->T[utt];
 }
 int batch_copy_probs(Batch* b, int utt, float* out) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (utt < 0 || utt >= b->B) return -1;
   const int C = b->e->hm.n_classes;
   CUDA_OK(cudaMemcpy(out, b->d_probs + (size_t)utt * b->T_cap * C, (size_t)b->T[utt] * C * 4, cudaMemcpyDeviceToHost));
   return b->T[utt];
 }
 int batch_set_probs64(Batch* b, const double* probs, const int* T, int B, int T_stride) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (B < 1 || B > b->B_cap) return -1;
   const int C = b->e->hm.n_classes;
   if (!b->d_probs64) CUDA_OK(cudaMalloc((void**)&b->d_probs64, (size_t)b->B_cap * b->T_cap * C * 8));
@@ -1331,6 +1345,7 @@ int batch_set_probs64(Batch* b, const double* probs, const int* T, int B, int T_
 }
 
 int batch_set_probs(Batch* b, const float* probs, const int* T, int B, int T_stride) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (B < 1 || B > b->B_cap) return -1;
   b->use_probs64 = false;
   const int C = b->e->hm.n_classes;
@@ -1348,6 +1363,7 @@ int batch_set_probs(Batch* b, const float* probs, const int* T, int B, int T_str
 
 // ====================================================================================== streaming (B == 1)
 int batch_stream_reset(Batch* b, int beam) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (beam < 1 || beam > b->beam_cap) return -1;
   Engine* e = b->e;
   b->B = 1;
@@ -1365,6 +1381,7 @@ int batch_stream_reset(Batch* b, int beam) {
 }
 
 int batch_stream_push_windows(Batch* b, const int16_t* windows, const int* n_valid, int n_windows, int n_zero_frames) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   Engine* e = b->e;
   const auto& m = e->hm;
   if (b->stream_frames + n_windows + n_zero_frames > b->rows_per_utt) return -2;
@@ -1395,6 +1412,7 @@ int batch_stream_push_windows(Batch* b, const int16_t* windows, const int* n_val
 }
 
 int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_probs) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   (void)keep_last_probs;
   Engine* e = b->e;
   const auto& m = e->hm;
@@ -1448,6 +1466,7 @@ int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_p
 }
 
 int batch_stream_decode(Batch* b, int num_results, std::vector<Decoded>* out) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (ensure_results_capacity(b, num_results)) return -1;
   if (decoder_finalize(b, 1, b->cur_beam, num_results)) return -1;
   CUDA_OK(cudaMemcpyAsync(b->h_out_mem, b->d_out_mem, b->out_bytes_per_utt, cudaMemcpyDeviceToHost, b->st));
@@ -1459,6 +1478,7 @@ int batch_stream_decode(Batch* b, int num_results, std::vector<Decoded>* out) {
 int batch_stream_frames(const Batch* b) { return b->stream_frames; }
 
 int batch_stream_last_probs(Batch* b, std::vector<double>* out, int* n_rows) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   const int C = b->e->hm.n_classes;
   std::vector<float> tmp((size_t)b->last_run_T * C);
   CUDA_OK(cudaMemcpy(tmp.data(), b->d_probs, tmp.size() * 4, cudaMemcpyDeviceToHost));

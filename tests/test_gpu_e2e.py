@@ -164,3 +164,21 @@ def test_batch_api_matches_single(model):
     pcms = [synth.make_pcm(n, utt=70 + i) for i, n in enumerate([16000, 8000, 24000, 1000, 16000])]
     batch_texts = m.sttBatch(pcms)
     assert batch_texts == [m.stt(p) for p in pcms]
+
+
+def test_batch_pipeline_matches_sequential(model):
+    """Two staged contexts driven from two host threads (stt_b200.BatchPipeline, what bench.py's e2e arm uses) return
+    the same transcripts, in submission order, as one context used sequentially."""
+    from stt_b200 import BatchPipeline, synth
+    m, _ = model
+    jobs = [[synth.make_pcm(8000 + 640 * (i + 3 * j), utt=900 + 10 * j + i) for i in range(4)] for j in range(5)]
+    b = m.createBatch(4, 20000)
+    want = []
+    for pcms in jobs:
+        b.upload(pcms)
+        b.forward()
+        b.decode(1)
+        b.fetch()
+        want.append(b.transcripts())
+    pipe = BatchPipeline(m, 4, 20000, depth=2)
+    assert pipe.map(jobs) == want
