@@ -913,6 +913,11 @@ int launch_lstm_pp_inst(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaS
   attrs[1].val.clusterDim.z = 1;
   cfgl.attrs = attrs;
   cfgl.numAttrs = 2;
+  // Nsight Compute (2025.2, driver 580) fails cooperative + cluster launches with "LaunchFailed".  For PROFILING runs
+  // only, STT_B200_LSTM_NONCOOP=1 drops the cooperative attribute: ncu serialises kernels, so the 128 one-per-SM CTAs
+  // are co-resident anyway; production launches keep the guarantee.
+  static const bool noncoop = getenv("STT_B200_LSTM_NONCOOP") != nullptr;
+  if (noncoop) { attrs[0] = attrs[1]; cfgl.numAttrs = 1; }
   if (usable < 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) { cudaGetLastError(); usable = 0; return 1; }
     int n_clusters = 0;
