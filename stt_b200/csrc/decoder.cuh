@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   __shared__ float s_logp2[2][kMaxClasses];
   __shared__ double s_logblank[2];
   __shared__ uint32_t s_gate[2];
-  __shared__ uint32_t s_hist[256];
+  __shared__ __align__(16) uint32_t s_hist[256];
   __shared__ uint32_t s_rs[2];
   __shared__ double s_nextp[kMaxClasses];   // next row of probabilities, fetched with cp.async (f32 rows use the first half)   // "a node was revived" flags of the last two commits
   __shared__ uint32_t s_cnt[kCommitRounds * (NT / 32) + 1];
@@ -606,7 +606,6 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
       if ((tid & 31) == 0) s_red[tid >> 5] = m;
     }
-    if (tid == 0) s_u[1] = 0;  // LM queue length
     start_expanding |= s_gate[cb];
     __syncthreads();
     PHASE_MARK(1);
@@ -628,34 +627,6 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     }
     PHASE_MARK(0);
 
-    // ---- phase 2b: LM terms of the live prefixes that will be extended by the space this step
-    if (p.has_scorer) {
-      for (uint32_t i = tid; i < n_live; i += NT) {
-        const float sc = L.score[i];
-        if (sc == kNegMax) continue;
-        if (full_beam && s_logp[p.space_id] + sc < min_cutoff) continue;
-        if (((sm.child[i] | L.mask[i]) >> p.space_id) & 1u) sm.lmq[atomicAdd(&s_u[1], 1u)] = i;
-      }
-      __syncthreads();
-      const uint32_t n_lm = s_u[1];
-      constexpr int NW = NT / 32;
-      for (uint32_t base = 0; base < n_lm; base += NT) {
-        const int w = tid >> 5, l = tid & 31;
-        const uint32_t q = base + (uint32_t)(l * NW + w);  // spread the items over the warps
-        if (q < n_lm) {
-          const uint32_t i = sm.lmq[q];
-          uint32_t wid, nw;
-          // (float)(cond * alpha): ctc_beam_search_decoder.cpp:239 (hot-word boost = 0)
-          double cond = lm_eval_node(s, p, L.node[i], &wid, &nw);
-          if (p.n_hot > 0) cond += (double)hot_word_boost(s, p, L.node[i], wid);
-          sm.lmterm[i] = (float)(cond * sv.alpha);
-          sm.lmwid[i] = wid;
-          atomicAdd(&s_u[6], nw);
-          atomicAdd(&s_u[7], 1u);
-        }
-      }
-      __syncthreads();
-    }
     PHASE_MARK(2);
 
     // ---- phase 4a: which children each live prefix creates (labels allowed by the dictionary, without a live child,
@@ -669,6 +640,20 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         if (i < n_live) {
           const float si = L.score[i];
           if (si != kNegMax) {
+            // LM term of a prefix that will be extended by the space this step (new child or pulled by a live one).
+            // No barrier of its own: threads without LM work go on to their label masks while these wait for the
+            // arena, and everybody meets at the scan below, which phase 3 / 4b (the readers of lmterm) follow.
+            if (p.has_scorer && (((sm.child[i] | L.mask[i]) >> p.space_id) & 1u) &&
+                !(full_beam && s_logp[p.space_id] + si < min_cutoff)) {
+              uint32_t wid, nw;
+              // (float)(cond * alpha): ctc_beam_search_decoder.cpp:239
+              double cond = lm_eval_node(s, p, L.node[i], &wid, &nw);
+              if (p.n_hot > 0) cond += (double)hot_word_boost(s, p, L.node[i], wid);
+              sm.lmterm[i] = (float)(cond * sv.alpha);
+              sm.lmwid[i] = wid;
+              atomicAdd(&s_u[6], nw);
+              atomicAdd(&s_u[7], 1u);
+            }
             allow = L.mask[i] & all_labels & ~sm.child[i];
             if (full_beam) {
               uint32_t m = allow;
@@ -830,13 +815,17 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         if (tid < 32) {
           // lane l owns bins [8l, 8l+8); find the bin where the count from the top crosses k_rem
           uint32_t hc[8];
+          {
+            uint4* hv = reinterpret_cast<uint4*>(&s_hist[tid * 8]);
+            const uint4 h0 = hv[0], h1 = hv[1];
+            hv[0] = make_uint4(0u, 0u, 0u, 0u);
+            hv[1] = make_uint4(0u, 0u, 0u, 0u);
+            hc[0] = h0.x; hc[1] = h0.y; hc[2] = h0.z; hc[3] = h0.w;
+            hc[4] = h1.x; hc[5] = h1.y; hc[6] = h1.z; hc[7] = h1.w;
+          }
           uint32_t mine = 0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            hc[q] = s_hist[tid * 8 + q];
-            s_hist[tid * 8 + q] = 0;
-            mine += hc[q];
-          }
+          for (int q = 0; q < 8; ++q) mine += hc[q];
           uint32_t suffix = mine;  // inclusive sum over lanes >= tid
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
