@@ -260,7 +260,7 @@ def main():
     #      Two staged batch contexts are kept in flight (stt_b200.BatchPipeline) so that a batch's H2D copy and the host
     #      work around it overlap the previous batch's kernels; every step still uploads its PCM and fetches its results.
     from stt_b200 import BatchPipeline
-    E2E_DEPTH = 2
+    E2E_DEPTH = int(os.environ.get("STT_BENCH_E2E_DEPTH", "2"))
     pipe = BatchPipeline(model, B, n_samples, depth=E2E_DEPTH)
     pinned = []
     for k in range(E2E_DEPTH):

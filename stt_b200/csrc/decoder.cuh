@@ -79,8 +79,7 @@ struct Slot {
   float* lm_sb;          // [arena_cap * kStateWords] state backoffs
   uint32_t* lm_meta;     // [arena_cap]  state length | oov distance << 8 | words in history (saturating) << 16
   // timestep tree (path_trie.h:17-37): ts node 0 is the root
-  uint32_t* ts_parent;   // [ts_cap]
-  uint32_t* ts_val;      // [ts_cap]
+  uint2* ts_tree;        // [ts_cap] {parent, absolute timestep}
   // live list as left by the last launch (the step kernel works on a shared-memory copy)
   float *score, *b_prev, *nb_prev;   // [beam_cap]
   uint32_t *node, *ts;               // [beam_cap]
@@ -382,8 +381,7 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start,
   s.nodes[0] = root;
   s.lm_meta[0] = kNone;
   s.ht_gen = ht_gen;
-  s.ts_parent[0] = kNone;
-  s.ts_val[0] = 0;
+  s.ts_tree[0] = make_uint2(kNone, 0u);
   s.score[0] = 0.f;
   s.b_prev[0] = 0.f;
   s.nb_prev[0] = kNegMax;
@@ -398,7 +396,7 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start,
 
 // ------------------------------------------------------------------------------------------------ step kernel
 // Block-wide exclusive scan of one count per thread; returns the thread's offset and the block total.
-template <int NT>
+template <int NT, bool kTrailingBarrier = true>
 __device__ __forceinline__ uint32_t block_scan(uint32_t cnt, uint32_t* warp_sums /*[NT/32 + 1]*/, uint32_t& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t incl = cnt;
@@ -422,7 +420,7 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t cnt, uint32_t* warp_sums
   __syncthreads();
   const uint32_t off = warp_sums[warp] + (incl - cnt);
   total = warp_sums[NT / 32];
-  __syncthreads();
+  if (kTrailingBarrier) __syncthreads();  // callers that scan again before another barrier need warp_sums intact
   return off;
 }
 
@@ -498,6 +496,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   // ---- load the live list left by the previous launch
   int cur = 0;
   uint32_t rescan = 1, cpar = 0;  // see phase 0 / phase 6
+  bool launch_start = true;
   if (tid == 0) { s_rs[0] = 0; s_rs[1] = 0; }
   for (uint32_t i = tid; i < n_live; i += NT) {
     LiveList<WC>& L = sm.live[0];
@@ -586,11 +585,20 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           const uint32_t pn = L.pnode[j];
           uint32_t pi = kNone;
           if (pn != kNone) {
-            pi = s.nodes[pn].live_slot;
+            if (launch_start) {
+              // Node::live_slot is only written when a launch ends, so it may be stale for a node that has left the
+              // beam since: believe it only if that slot really holds the parent
+              pi = s.nodes[pn].live_slot;
+              if (pi >= n_live || L.node[pi] != pn) pi = kNone;
+            } else {
+              for (uint32_t i = 0; i < n_live; ++i)   // more revivals than the announcement list holds: search
+                if (L.node[i] == pn) pi = i;
+            }
             if (pi != kNone) atomicOr(&sm.child[pi], 1u << L.chr[j]);
           }
           sm.plive[j] = pi;
         }
+        launch_start = false;
       } else {
         // the last commit left every prefix's parent slot in plive (old slot -> new slot map, phase 6)
         for (uint32_t j = tid; j < n_live; j += NT) {
@@ -666,7 +674,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           }
         }
         uint32_t total;
-        const uint32_t off = run_base + block_scan<NT>(__popc(allow), s_warp, total);
+        const uint32_t off = run_base + block_scan<NT, (WC > NT)>(__popc(allow), s_warp, total);
         if (i < n_live) {
           sm.child[i] = allow;   // the live-child masks are no longer needed (phase 3 uses plive)
           sm.lmq[i] = off;       // reuse: offset of this prefix's first child among the new candidates
@@ -921,16 +929,14 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
             const uint32_t tp = sm.tsprev[e];
             if (tp != kNone) {
               const uint32_t id = ts_count + pos;
-              if (id < s.ts_cap) { s.ts_parent[id] = tp; s.ts_val[id] = abs_t; }
+              if (id < s.ts_cap) s.ts_tree[id] = make_uint2(tp, abs_t);
               Nx.ts[pos] = id;
             } else {
               Nx.ts[pos] = L.ts[e];
             }
-            s.nodes[nd].live_slot = pos;
             sm.lmq[pos] = 0x80000000u | e;  // not a new node: remember the old slot
             sm.tsprev[e] = pos;             // tsprev now maps old live slot -> new live slot (kNone = pruned)
           } else {
-            s.nodes[nd].live_slot = kNone;
             sm.tsprev[e] = kNone;
           }
         } else if (keep) {
@@ -938,7 +944,11 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           Nx.score[pos] = lp;
           Nx.b[pos] = kNegMax;
           Nx.nb[pos] = lp;
-          sm.lmq[pos] = P0[e];  // parent live index | label << 16
+          const uint32_t pk = P0[e];
+          sm.lmq[pos] = pk;  // parent live index | label << 16
+          // the (parent,label) hash slot is a DRAM miss: start it now, (ii) touches it after the barrier
+          const unsigned long long hw = ht_pack(s.ht_gen, L.node[pk & 0xffffu], (pk >> 16) & 0xffu, 0u);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(s.ht + (ht_hash(hw >> 24) & s.ht_mask)));
         }
       }
       out_base += s_cnt[kCommitRounds * (NT / 32)];
@@ -973,7 +983,6 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       if ((cmL[pi] >> c) & 1u) {  // this child existed before (rare): find it, it is revived under its old identity
         id = ht_find_existing(s, pnode, c);
         own_mask = *reinterpret_cast<volatile uint32_t*>(&s.nodes[id].child_mask);
-        s.nodes[id].live_slot = pos;
         const uint32_t ri = atomicAdd(&s_rs[cpar], 1u);   // tell the live children of this node where it sits now
         if (ri < (uint32_t)kRevCap) rev[ri] = make_uint2(id, pos);
       }
@@ -1004,7 +1013,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       cmN[pos] = own_mask;
       if (lp > kNegMax) {  // "prefix_new->log_prob_nb_cur < log_p" (:246-251)
         const uint32_t tid2 = ts_count + pos;
-        if (tid2 < s.ts_cap) { s.ts_parent[tid2] = L.ts[pi]; s.ts_val[tid2] = abs_t; }
+        if (tid2 < s.ts_cap) s.ts_tree[tid2] = make_uint2(L.ts[pi], abs_t);
         Nx.ts[pos] = tid2;
       } else {
         Nx.ts[pos] = kNone;
@@ -1052,6 +1061,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       s.nb_prev[i] = L.nb[i];
       s.node[i] = L.node[i];
       s.ts[i] = L.ts[i];
+      s.nodes[L.node[i]].live_slot = i;   // read (and validated) by the next launch's first expanding step
     }
   }
   if (tid == 0) {
@@ -1138,11 +1148,11 @@ __global__ void __launch_bounds__(NT) decoder_finalize_kernel(Slot* slots, const
       }
       const uint32_t tn = s.ts[i];
       int tlen = 0;
-      for (uint32_t w = tn; w != kNone && w != 0; w = s.ts_parent[w]) ++tlen;
+      for (uint32_t w = tn; w != kNone && w != 0; w = s.ts_tree[w].x) ++tlen;
       k = tlen;
-      for (uint32_t w = tn; w != kNone && w != 0; w = s.ts_parent[w]) {
+      for (uint32_t w = tn; w != kNone && w != 0; w = s.ts_tree[w].x) {
         --k;
-        if (k < o.max_tokens) o.timesteps[(size_t)r * o.max_tokens + k] = s.ts_val[w];
+        if (k < o.max_tokens) o.timesteps[(size_t)r * o.max_tokens + k] = s.ts_tree[w].y;
       }
     }
     __syncthreads();

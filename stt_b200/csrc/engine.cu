@@ -606,7 +606,7 @@ int alloc_slots(Batch* b) {
   const size_t o_ht = take(8ull * ht);
   const size_t o_lmc = take(8ull * arena_cap), o_lmsw = take(4ull * arena_cap * SW), o_lmsb = take(4ull * arena_cap * SW);
   const size_t o_lmm = take(4ull * arena_cap);
-  const size_t o_tsp = take(4ull * ts_cap), o_tsv = take(4ull * ts_cap);
+  const size_t o_tstree = take(8ull * ts_cap);
   const size_t o_sc = take(4ull * W), o_bp = take(4ull * W), o_nb = take(4ull * W), o_nd = take(4ull * W), o_lts = take(4ull * W);
   const size_t o_ck = take(8ull * cand_cap), o_p0 = take(4ull * cand_cap), o_p1 = take(4ull * cand_cap);
   const size_t o_scal = take(64), o_ph = take(64), o_aux = take(W > 512 ? 16ull * 2048 : 256);  // StepSmem::aux of the wide instantiation (WC = 2048)
@@ -623,7 +623,7 @@ int alloc_slots(Batch* b) {
     s.ht_gen = 0;
     s.lm_cond = (double*)(base + o_lmc); s.lm_sw = (uint32_t*)(base + o_lmsw); s.lm_sb = (float*)(base + o_lmsb);
     s.lm_meta = (uint32_t*)(base + o_lmm);
-    s.ts_parent = (uint32_t*)(base + o_tsp); s.ts_val = (uint32_t*)(base + o_tsv);
+    s.ts_tree = (uint2*)(base + o_tstree);
     s.score = (float*)(base + o_sc); s.b_prev = (float*)(base + o_bp); s.nb_prev = (float*)(base + o_nb);
     s.node = (uint32_t*)(base + o_nd); s.ts = (uint32_t*)(base + o_lts);
     s.c_key = (unsigned long long*)(base + o_ck); s.c_p0 = (uint32_t*)(base + o_p0); s.c_p1 = (uint32_t*)(base + o_p1);
