@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   __shared__ uint32_t s_gate[2];
   __shared__ __align__(16) uint32_t s_hist[256];
   __shared__ uint32_t s_rs[2];
+  __shared__ uint32_t s_bm[32];  // 1024-bit filter over the ids of the nodes revived by the current commit
   __shared__ double s_nextp[kMaxClasses];   // next row of probabilities, fetched with cp.async (f32 rows use the first half)   // "a node was revived" flags of the last two commits
   __shared__ uint32_t s_cnt[kCommitRounds * (NT / 32) + 1];
   __shared__ uint32_t s_warp[NT / 32 + 1];
@@ -867,6 +868,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
 
     // ---- phase 6: order-preserving compaction + commit (iterate_to_vec :159-190, remove :192-209)
     if (tid == 0) s_u[5] = arena_count;
+    if (tid < 32) s_bm[tid] = 0;
     // (i) shared-memory-only compaction, in candidate order (live entries precede new ones): survivors get their slot
     //     in the next live list; a new survivor parks (parent index, label) there.  Up to kCommitRounds rounds of NT
     //     candidates share ONE scan: per-round warp ballots, a 128-entry scan of the warp counts by warp 0.
@@ -985,6 +987,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         own_mask = *reinterpret_cast<volatile uint32_t*>(&s.nodes[id].child_mask);
         const uint32_t ri = atomicAdd(&s_rs[cpar], 1u);   // tell the live children of this node where it sits now
         if (ri < (uint32_t)kRevCap) rev[ri] = make_uint2(id, pos);
+        atomicOr(&s_bm[(id >> 5) & 31u], 1u << (id & 31u));
       }
       const uint32_t cord = (is_space || !p.fst_space_skip) ? 0u : ordL[pi] + (uint32_t)arc.w;
       const float lp = Nx.score[pos];
@@ -1031,9 +1034,12 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         uint32_t pl = my_plive[r];
         if (pl == kNone && n_rev != 0 && !rescan && (sm.lmq[pos] & 0x80000000u)) {
           const uint32_t pn = Nx.pnode[pos];
-          for (uint32_t k = 0; k < n_rev; ++k) {
-            const uint2 rv = rev[k];
-            if (rv.x == pn) pl = rv.y;
+          // most orphans' parents were not revived: a 1024-bit filter spares them the walk over the announcements
+          if (pn != kNone && ((s_bm[(pn >> 5) & 31u] >> (pn & 31u)) & 1u)) {
+            for (uint32_t k = 0; k < n_rev; ++k) {
+              const uint2 rv = rev[k];
+              if (rv.x == pn) { pl = rv.y; break; }
+            }
           }
         }
         sm.plive[pos] = pl;
