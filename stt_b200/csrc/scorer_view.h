@@ -180,19 +180,35 @@ STT_HD void unigram_find(const ScorerView& v, uint32_t word, NodeRange& next, fl
   next.end = load_u64(u + 24);
 }
 
-// FindBitPacked: records [begin, end) hold strictly increasing word ids.
+// FindBitPacked (trie.cc:32-40 -> bit_packing / UniformFind, sorted_uniform.hh:60-90): records [begin, end) hold
+// strictly increasing word ids; which probe sequence finds the record does not change the answer.  Like KenLM this is
+// an interpolation search: word ids are ranks of 64-bit hashes, so the ids of a node's children are uniform in
+// [0, max_word] and ~log log n probes suffice where bisection needs log n -- every probe is a dependent memory access.
 STT_HD bool find_bit_packed(const uint8_t* base, uint64_t word_mask, uint8_t total_bits, uint64_t begin,
-                            uint64_t end, uint64_t key, uint64_t& at) {
-  uint64_t lo = begin, hi = end;
-  while (lo < hi) {
-    uint64_t mid = (lo + hi) >> 1;
-    uint64_t k = read_int57(base, mid * total_bits, word_mask);
-    if (k < key) lo = mid + 1;
-    else hi = mid;
-  }
-  if (lo < end && read_int57(base, lo * total_bits, word_mask) == key) {
-    at = lo;
-    return true;
+                            uint64_t end, uint64_t key, uint64_t max_word, uint64_t& at) {
+  // invariant: key can only be at an index in (before_it, after_it); record(before_it) = before_v < key < after_v
+  uint64_t before_it = begin - 1, after_it = end;   // begin >= 0; "begin - 1" is only ever compared, never read
+  uint64_t before_v = 0, after_v = max_word;
+  if (key > max_word) return false;
+  while (after_it - before_it > 1) {
+    const uint64_t span = after_it - before_it - 1;
+    uint64_t pivot;
+    if (span < (1ull << 31) && after_v - before_v < (1ull << 32)) {
+      pivot = before_it + 1 + (key - before_v) * span / (after_v - before_v + 1);
+    } else {
+      pivot = before_it + 1 + (span >> 1);
+    }
+    const uint64_t k = read_int57(base, pivot * total_bits, word_mask);
+    if (k < key) {
+      before_it = pivot;
+      before_v = k;
+    } else if (k > key) {
+      after_it = pivot;
+      after_v = k;
+    } else {
+      at = pivot;
+      return true;
+    }
   }
   return false;
 }
@@ -228,7 +244,7 @@ STT_HD bool middle_find(const ScorerView& v, int order_minus_2, uint32_t word, N
   const MiddleView& m = v.middle[order_minus_2];
   const uint8_t* base = v.blob + m.records_off;
   uint64_t at;
-  if (!find_bit_packed(base, m.word_mask, m.total_bits, node.begin, node.end, word, at)) return false;
+  if (!find_bit_packed(base, m.word_mask, m.total_bits, node.begin, node.end, word, v.vocab_count + 1, at)) return false;
   uint64_t bit = at * m.total_bits + m.word_bits;
   if (v.quantized) {
     const uint32_t bmask = (1u << v.backoff_bits) - 1, pmask = (1u << v.prob_bits) - 1;
@@ -250,7 +266,7 @@ STT_HD bool longest_find(const ScorerView& v, uint32_t word, const NodeRange& no
   const LongestView& l = v.longest;
   const uint8_t* base = v.blob + l.records_off;
   uint64_t at;
-  if (!find_bit_packed(base, l.word_mask, l.total_bits, node.begin, node.end, word, at)) return false;
+  if (!find_bit_packed(base, l.word_mask, l.total_bits, node.begin, node.end, word, v.vocab_count + 1, at)) return false;
   uint64_t bit = at * l.total_bits + l.word_bits;
   if (v.quantized) {
     uint32_t pcode = read_int25(base, bit, (1u << v.prob_bits) - 1);
