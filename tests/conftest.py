@@ -11,6 +11,8 @@ sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 SCORER = os.path.join(GOLDEN, "pruned_lm.scorer")  # data/smoke_test/pruned_lm.scorer of the reference (fixture data)
 VOCAB = os.path.join(GOLDEN, "vocab.pruned.txt")
+# data/smoke_test/LDC93S1_pcms16le_1_16000.wav of the reference: the utterance of BASELINE.json configs[0]
+LDC93S1_WAV = os.path.join(GOLDEN, "LDC93S1_pcms16le_1_16000.wav")
 
 
 def pytest_configure(config):
@@ -71,3 +73,14 @@ def small_model(tmp_path_factory):
     p = tmp_path_factory.mktemp("model") / "small.sttw"
     synth.write_model(str(p), w)
     return str(p), w
+
+
+@pytest.fixture(scope="session")
+def ldc93s1_pcm():
+    """int16 samples of the reference's smoke-test utterance (46 797 samples @ 16 kHz -> 146 timesteps)."""
+    import wave
+    with wave.open(LDC93S1_WAV, "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate()) == (1, 2, 16000)
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").copy()
+    assert pcm.size == 46797
+    return pcm

@@ -61,3 +61,19 @@ def test_cli_errors(small_model, tmp_path):
     assert r.returncode != 0 and "Could not create model" in r.stderr
     r = subprocess.run([CLI, "--model", path, "--audio", "x.wav", "--stream", "100"], capture_output=True, text=True)
     assert "multiples of 160" in r.stdout
+
+
+def test_cli_on_the_reference_smoke_test_wav(small_model):
+    """asserts.sh runs `stt --model ... --audio LDC93S1_pcms16le_1_16000.wav`: the CLI's WAV reader on the reference's
+    own file (a 44-byte canonical header here, but parsed chunk by chunk) must feed exactly the samples the library sees."""
+    from conftest import LDC93S1_WAV
+    from stt_b200 import Model
+    import wave
+    path, _ = small_model
+    with wave.open(LDC93S1_WAV, "rb") as w:
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+    m = Model(path)
+    m.setBeamWidth(64)
+    m.enableExternalScorer(SCORER)
+    base = ["--model", path, "--scorer", SCORER, "--audio", LDC93S1_WAV, "--beam_width", "64"]
+    assert _run(*base)[0].strip().split("\n")[-1] == m.stt(pcm)

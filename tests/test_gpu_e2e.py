@@ -182,3 +182,19 @@ def test_batch_pipeline_matches_sequential(model):
         want.append(b.transcripts())
     pipe = BatchPipeline(m, 4, 20000, depth=2)
     assert pipe.map(jobs) == want
+
+
+def test_real_speech_end_to_end(ref_decoder, model, english, ldc93s1_pcm):
+    """BASELINE configs[0] through the C ABI: STT_SpeechToText, the streaming API in 20 ms chunks and the batch API
+    agree on the reference's LDC93S1 recording, and equal the reference decoder run on the GPU's probabilities."""
+    m, _ = model
+    text = m.stt(ldc93s1_pcm)
+    st = m.createStream()
+    for o in range(0, ldc93s1_pcm.size, 320):
+        st.feedAudioContent(ldc93s1_pcm[o:o + 320])
+    assert st.finishStream() == text
+    assert m.sttBatch([ldc93s1_pcm]) == [text]
+    b = m.createBatch(1, ldc93s1_pcm.size)
+    b.upload([ldc93s1_pcm])
+    b.forward()
+    assert _ref_text(ref_decoder, b.probs(0), 64, english)[0] == text

@@ -108,3 +108,19 @@ def test_am_large_batch_uses_pair_kernel_and_matches_single(small_model):
         b1.upload([pcms[i]])
         b1.forward()
         np.testing.assert_array_equal(b.probs(i), b1.probs(0))
+
+
+def test_real_speech_features_and_probs(oracle, small_model, ldc93s1_pcm):
+    """BASELINE configs[0] on the GPU: the reference's LDC93S1 recording (real speech: silences, plosives, 60 dB of
+    dynamic range) through MFCC and the acoustic model, against the oracle."""
+    from stt_b200 import Model
+    path, w = small_model
+    m = Model(path)
+    b = m.createBatch(1, ldc93s1_pcm.size)
+    b.upload([ldc93s1_pcm])
+    b.forward()
+    T_ref, mfcc_ref = oracle.features_only(ldc93s1_pcm)
+    assert b.timesteps(0) == T_ref == 146
+    np.testing.assert_allclose(b.features(0), mfcc_ref, atol=MFCC_ATOL, rtol=1e-5)
+    probs_ref, _ = oracle.PortAM(w).stream(ldc93s1_pcm)
+    assert np.abs(b.probs(0) - probs_ref).max() <= PROBS_ATOL

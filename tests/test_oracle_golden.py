@@ -88,3 +88,12 @@ def test_kenlm_known_answer(ref_decoder):
     o = ref_decoder
     sc = o.RefScorer(SCORER, o.RefAlphabet(synth.ENGLISH_LABELS))
     assert abs(sc.log_cond_prob(["she", "had"], True) - (-0.970070)) < 1e-6
+
+
+def test_real_utterance_frame_count_and_feature_range(oracle, ldc93s1_pcm):
+    """BASELINE configs[0] plumbing on REAL speech (the reference's LDC93S1 clip): 46 797 samples -> 146 timesteps
+    (SURVEY 8c known answer); features are finite and span the dynamic range speech has and synthetic tones do not."""
+    T, feats = oracle.features_only(ldc93s1_pcm)
+    assert T == 146 and feats.shape == (146, 26)
+    assert np.isfinite(feats).all()
+    assert feats[:, 0].max() - feats[:, 0].min() > 5.0   # C0 follows the energy contour of the utterance
