@@ -234,39 +234,74 @@ __device__ double lm_window_cond(const Slot& s, const sttscorer::ScorerView& v, 
   return sttscorer::log_cond_prob_ids(v, ids, n, n < order);
 }
 
+constexpr uint32_t kStopUnknown = 0xfffffffdu;  // lm_eval_node: the caller does not have the node's last_space at hand
+
 // Cached evaluation of get_log_cond_prob(make_ngram(prefix `node`), bos) -- see Slot::lm_cond.
-__device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t node, uint32_t* word_out,
+//   * the id of the word ending at `node` was resolved when the node was created (Node::lm_wid, phase 6);
+//   * the KenLM state BEFORE that word -- the state after the previous word -- was copied into the lm_* arrays of the
+//     space node that separates the two words when that space node was created (phase 6), so it sits at index `stop`
+//     (= the node's last_space, which the caller has in shared memory): every load below is independent of the others
+//     and a first evaluation starts the trie descent after ONE round trip.
+__device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t node, uint32_t stop_hint, uint32_t* word_out,
                                uint32_t* n_window_out) {
   const sttscorer::ScorerView& v = p.scorer;
   const int order = (int)v.order;
-  // the three loads are independent: a cached node costs one round trip
-  const uint32_t meta0 = s.lm_meta[node];   // kNone = not computed yet
+  const uint32_t meta0 = s.lm_meta[node];   // kNone = not computed yet (space nodes: the carried context, see above)
   const double cond0 = s.lm_cond[node];
   const Node nd = s.nodes[node];
+  uint32_t stop = stop_hint;
+  uint32_t cmeta = kNone;
+  uint32_t csw[kStateWords];
+  float csb[kStateWords];
+  if (stop_hint != kStopUnknown && stop_hint != kNone) {
+    cmeta = s.lm_meta[stop_hint];
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) {
+      csw[i] = s.lm_sw[(size_t)stop_hint * kStateWords + i];
+      csb[i] = s.lm_sb[(size_t)stop_hint * kStateWords + i];
+    }
+  }
+  const uint32_t cc = nd.chr;
+  if (cc == kRootChar) {
+    // empty prefix: make_ngram returns no words, get_log_cond_prob of nothing is 0 (scorer.cpp:325,343)
+    *word_out = 0;
+    *n_window_out = 0;
+    return 0.0;
+  }
+  if (stop == kStopUnknown) {
+    stop = nd.last_space;  // == node when node is itself a space (empty word)
+    if (stop != kNone) {
+      cmeta = s.lm_meta[stop];
+#pragma unroll
+      for (int i = 0; i < kStateWords; ++i) {
+        csw[i] = s.lm_sw[(size_t)stop * kStateWords + i];
+        csb[i] = s.lm_sb[(size_t)stop * kStateWords + i];
+      }
+    }
+  }
+  if (cc == (uint32_t)v.space_label) {
+    // a prefix that ends with a space names an empty word: never in the vocabulary, OOV_SCORE undivided
+    // (scorer.cpp:328-331).  Nothing is cached: this node's lm_* arrays hold the context for the NEXT word.
+    const uint32_t cw = (cmeta == kNone) ? 0u : (cmeta >> 16);
+    const uint32_t nw = cw >= 0xfffeu ? 0xffffu : cw + 1;
+    *word_out = 0;
+    *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
+    return -1000.0;
+  }
   if (meta0 != kNone) {
     *word_out = nd.lm_wid;
     const uint32_t nw = meta0 >> 16;
     *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
     return cond0;
   }
-  const uint32_t cc = nd.chr;
-  double cond;
-  uint32_t wid = 0, meta;
-  sttscorer::LmState out;
-  out.length = 0;
-  if (cc == kRootChar) {
-    // empty prefix: make_ngram returns no words, get_log_cond_prob of nothing is 0 (scorer.cpp:325,343)
-    cond = 0.0;
-    sttscorer::begin_sentence_state(v, out);
-    meta = (uint32_t)out.length | (255u << 8) | (0u << 16);
-  } else {
-    // ---- the word ending at `node`
-    const uint32_t stop = nd.last_space;  // == node when node is itself a space (empty word)
+  // ---- the word ending at `node`
+  uint32_t wid = nd.lm_wid;
+  if (wid == kNone) {
     uint32_t sk = kNone;
-    if (cc != (uint32_t)v.space_label && p.fst_space_skip) sk = __ldg(p.fst_space_skip + nd.dict);
+    if (p.fst_space_skip) sk = __ldg(p.fst_space_skip + nd.dict);
     if (sk != kNone) {
       wid = __ldg(p.ord2wid + nd.ord + sk);
-    } else if (cc != (uint32_t)v.space_label) {
+    } else {
       uint8_t buf[kMaxWordBytes];
       int len = 0;
       bool too_long = false;
@@ -283,56 +318,47 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
       for (int a = 0, b = len - 1; a < b; ++a, --b) { const uint8_t t = buf[a]; buf[a] = buf[b]; buf[b] = t; }
       wid = too_long ? 0u : sttscorer::vocab_index(v, buf, (uint32_t)len);
     }
-    // ---- history state: the word-final node before the space that precedes this word
-    sttscorer::LmState ctx;
-    uint32_t ctx_oov = 255, ctx_words = 0;
-    bool have_ctx = true;
-    if (stop == kNone) {
-      sttscorer::begin_sentence_state(v, ctx);
-    } else {
-      const uint32_t prev_end = s.nodes[stop].parent;
-      const Node pe = s.nodes[prev_end];
-      if (pe.chr == kRootChar || pe.chr == (uint32_t)v.space_label) {
-        // the previous "word" is empty (leading / double space): it is an OOV inside the window
-        sttscorer::null_context_state(ctx);
-        ctx_oov = 0;
-        ctx_words = 1;
-      } else if (pe.lm_wid != kNone) {
-        const uint32_t m = s.lm_meta[prev_end];
-        ctx.length = (uint8_t)(m & 0xffu);
-        ctx_oov = (m >> 8) & 0xffu;
-        ctx_words = m >> 16;
-        for (int i = 0; i < (int)ctx.length; ++i) {
-          ctx.words[i] = s.lm_sw[(size_t)prev_end * kStateWords + i];
-          ctx.backoff[i] = s.lm_sb[(size_t)prev_end * kStateWords + i];
-        }
-      } else {
-        have_ctx = false;
-      }
-    }
-    if (!have_ctx) return lm_window_cond(s, v, node, word_out, n_window_out);  // not cached: no state to carry
-    uint32_t oov_dist;
-    if (wid == 0) {
-      sttscorer::null_context_state(out);
-      oov_dist = 0;
-      cond = -1000.0;  // OOV_SCORE, returned undivided (scorer.cpp:328-331)
-    } else {
-      const float p10 = sttscorer::full_score(v, ctx, wid, out);
-      oov_dist = ctx_oov >= 254 ? 255u : ctx_oov + 1;
-      // an OOV word among the previous order-1 words is still inside the reference's window
-      cond = (oov_dist <= (uint32_t)(order - 1)) ? -1000.0 : (double)p10 / (double)0.4342944819f;
-    }
-    const uint32_t nwords = ctx_words >= 0xfffeu ? 0xffffu : ctx_words + 1;
-    meta = (uint32_t)out.length | (oov_dist << 8) | (nwords << 16);
   }
+  // ---- history state
+  sttscorer::LmState ctx;
+  uint32_t ctx_oov = 255, ctx_words = 0;
+  if (stop == kNone) {
+    sttscorer::begin_sentence_state(v, ctx);
+  } else if (cmeta != kNone) {
+    ctx.length = (uint8_t)(cmeta & 0xffu);
+    ctx_oov = (cmeta >> 8) & 0xffu;
+    ctx_words = cmeta >> 16;
+#pragma unroll
+    for (int i = 0; i < kStateWords; ++i) {
+      ctx.words[i] = csw[i];
+      ctx.backoff[i] = csb[i];
+    }
+  } else {
+    return lm_window_cond(s, v, node, word_out, n_window_out);  // no carried state (not expected): the literal way
+  }
+  double cond;
+  sttscorer::LmState out;
+  out.length = 0;
+  uint32_t oov_dist;
+  if (wid == 0) {
+    sttscorer::null_context_state(out);
+    oov_dist = 0;
+    cond = -1000.0;  // OOV_SCORE, returned undivided (scorer.cpp:328-331)
+  } else {
+    const float p10 = sttscorer::full_score(v, ctx, wid, out);
+    oov_dist = ctx_oov >= 254 ? 255u : ctx_oov + 1;
+    // an OOV word among the previous order-1 words is still inside the reference's window
+    cond = (oov_dist <= (uint32_t)(order - 1)) ? -1000.0 : (double)p10 / (double)0.4342944819f;
+  }
+  const uint32_t nwords = ctx_words >= 0xfffeu ? 0xffffu : ctx_words + 1;
+  const uint32_t meta = (uint32_t)out.length | (oov_dist << 8) | (nwords << 16);
   for (int i = 0; i < (int)out.length; ++i) {
     s.lm_sw[(size_t)node * kStateWords + i] = out.words[i];
     s.lm_sb[(size_t)node * kStateWords + i] = out.backoff[i];
   }
   s.lm_meta[node] = meta;
   s.lm_cond[node] = cond;
-  __threadfence_block();
-  s.nodes[node].lm_wid = wid;
+  if (nd.lm_wid == kNone) s.nodes[node].lm_wid = wid;
   *word_out = wid;
   const uint32_t nw = meta >> 16;
   *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
@@ -656,7 +682,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
                 !(full_beam && s_logp[p.space_id] + si < min_cutoff)) {
               uint32_t wid, nw;
               // (float)(cond * alpha): ctc_beam_search_decoder.cpp:239
-              double cond = lm_eval_node(s, p, L.node[i], &wid, &nw);
+              double cond = lm_eval_node(s, p, L.node[i], L.lsp[i], &wid, &nw);
               if (p.n_hot > 0) cond += (double)hot_word_boost(s, p, L.node[i], wid);
               sm.lmterm[i] = (float)(cond * sv.alpha);
               sm.lmwid[i] = wid;
@@ -980,7 +1006,8 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       const uint32_t np = sm.tsprev[pi];   // the parent's slot in the next live list, if it survived
       my_plive[r] = np;
       int4 arc = make_int4(0, 0, (int)all_labels, 0);
-      if (p.has_scorer) arc = __ldg(&p.fst_arc4[L.pos[pi] + __popc(L.mask[pi] & ((1u << c) - 1u))]);
+      const uint32_t ai = p.has_scorer ? (L.pos[pi] + __popc(L.mask[pi] & ((1u << c) - 1u))) : 0u;
+      if (p.has_scorer) arc = __ldg(&p.fst_arc4[2 * ai]);
       uint32_t id = kNone, own_mask = 0;
       if ((cmL[pi] >> c) & 1u) {  // this child existed before (rare): find it, it is revived under its old identity
         id = ht_find_existing(s, pnode, c);
@@ -998,8 +1025,29 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           n.parent = pnode; n.chr = c; n.dict = arc.x; n.last_space = is_space ? id : L.lsp[pi];
           n.word_id = is_space ? (p.has_scorer ? sm.lmwid[pi] : 0u) : cord;
           n.live_slot = pos; n.lm_wid = kNone; n.child_mask = 0;
+          uint32_t meta_init = kNone;  // LM cache of this node: not computed
+          if (p.has_scorer) {
+            if (is_space) {
+              // the KenLM state after the word that this space terminates = the context of the next word: carried here
+              // so that the next word's first evaluation finds it without walking back (lm_eval_node)
+              const uint32_t pc = L.chr[pi];
+              if (pc == (uint32_t)(uint8_t)kRootChar || (int)pc == p.space_id) {
+                meta_init = 0u | (0u << 8) | (1u << 16);  // empty previous word: null context, an OOV inside the window
+              } else {
+                meta_init = s.lm_meta[pnode];
+                const uint32_t len = meta_init == kNone ? 0u : (meta_init & 0xffu);
+                for (uint32_t q = 0; q < len && q < (uint32_t)kStateWords; ++q) {
+                  s.lm_sw[(size_t)id * kStateWords + q] = s.lm_sw[(size_t)pnode * kStateWords + q];
+                  s.lm_sb[(size_t)id * kStateWords + q] = s.lm_sb[(size_t)pnode * kStateWords + q];
+                }
+              }
+            } else if (p.fst_space_skip) {
+              const uint32_t css = (uint32_t)__ldg(&p.fst_arc4[2 * ai + 1]).x;  // skip of the child's own space arc
+              if (css != kNone) n.lm_wid = __ldg(p.ord2wid + cord + css);       // the word that would end here
+            }
+          }
           s.nodes[id] = n;
-          s.lm_meta[id] = kNone;  // LM cache of this node: not computed
+          s.lm_meta[id] = meta_init;
           ht_insert(s, pnode, c, id);
           atomicOr(&s.nodes[pnode].child_mask, 1u << c);
           if (np != kNone) atomicOr(&cmN[np], 1u << c);
@@ -1113,7 +1161,7 @@ __global__ void __launch_bounds__(NT) decoder_finalize_kernel(Slot* slots, const
     const uint32_t c = s.nodes[nd].chr;
     if (p.has_scorer && i < (uint32_t)p.beam && c != kRootChar && (int)c != p.space_id) {
       uint32_t wid_unused, nw_unused;
-      float add = (float)(lm_eval_node(s, p, nd, &wid_unused, &nw_unused) * p.scorer.alpha);
+      float add = (float)(lm_eval_node(s, p, nd, kStopUnknown, &wid_unused, &nw_unused) * p.scorer.alpha);
       add = (float)((double)add + p.scorer.beta);
       sc = sc + add;
     }

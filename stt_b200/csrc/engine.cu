@@ -357,7 +357,8 @@ void engine_destroy(Engine* e) {
 // arc_skip along a word's arcs is its rank among the FST's words in label order.  ord2wid maps that rank to the KenLM
 // vocabulary id of the word's bytes (the same vocab_index the walking path calls).  Anything unexpected -- a cycle, a
 // word that does not end with the space label, more than 2^31 words -- leaves the tables null (walking path).
-void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_t* bytes, std::vector<uint32_t>* skip_out) {
+void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_t* bytes, std::vector<uint32_t>* skip_out,
+                         std::vector<uint32_t>* space_skip_out) {
   const int64_t nS = v.fst_nstates, nA = v.fst_narcs;
   if (nS <= 0 || nA <= 0 || v.fst_start < 0 || v.fst_start >= nS) return;
   struct Arc { int32_t il, nx; };
@@ -459,6 +460,7 @@ void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_
   cudaMemcpy(e->fst_space_skip, space_skip.data(), space_skip.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(e->ord2wid, o2w.data(), o2w.size() * 4, cudaMemcpyHostToDevice);
   *skip_out = std::move(skip);
+  *space_skip_out = std::move(space_skip);
   if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] dictionary word ordinals: %llu words\n", (unsigned long long)n_words);
 }
 
@@ -505,12 +507,15 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
       }
       st2[(size_t)q] = make_uint2(pos, mask);
     }
-    std::vector<uint32_t> skip;
-    build_word_ordinals(e, v, bytes, &skip);
-    std::vector<int4> ar4(ar2.size());
+    std::vector<uint32_t> skip, space_skip;
+    build_word_ordinals(e, v, bytes, &skip, &space_skip);
+    // two 16-byte words per arc: {child state, child's first arc, child's label mask, ordinal skip} and
+    // {ordinal skip of the CHILD state's space arc (or none), -, -, -}
+    std::vector<int4> ar4(2 * ar2.size());
     for (size_t i = 0; i < ar2.size(); ++i) {
       const uint2 cs = st2[(size_t)ar2[i].y];
-      ar4[i] = make_int4(ar2[i].y, (int)cs.x, (int)cs.y, skip.empty() ? 0 : (int)skip[i]);
+      ar4[2 * i] = make_int4(ar2[i].y, (int)cs.x, (int)cs.y, skip.empty() ? 0 : (int)skip[i]);
+      ar4[2 * i + 1] = make_int4(space_skip.empty() ? -1 : (int)space_skip[(size_t)ar2[i].y], 0, 0, 0);
     }
     if (cudaMalloc(reinterpret_cast<void**>(&e->fst_state2), std::max<size_t>(st2.size(), 1) * sizeof(uint2)) != cudaSuccess ||
         cudaMalloc(reinterpret_cast<void**>(&e->fst_arc4), std::max<size_t>(ar4.size(), 1) * sizeof(int4)) != cudaSuccess)
