@@ -169,6 +169,7 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
       inline_bits = required_bits(max_next);
     }
     m.records_off = p + bhiksha_size;
+    m.n_records = entries;
     m.word_bits = word_bits;
     m.word_mask = word_mask;
     m.quant_bits = middle_quant_bits;

@@ -34,6 +34,7 @@ struct MiddleView {
   uint64_t records_off;   // byte offset of the bit-packed record array (BitPacked::base_)
   uint64_t offsets_off;   // ArrayBhiksha offset_begin_ (8-aligned, after its 8-byte header); 0 if DontBhiksha
   uint64_t offsets_count; // ArrayBhiksha offset_end_ - offset_begin_
+  uint64_t n_records;     // n-grams of this order (record indices run 0..n_records)
   uint64_t word_mask, next_mask;
   uint8_t word_bits, total_bits, quant_bits, next_bits;
 };
@@ -220,11 +221,19 @@ STT_HD void read_next(const ScorerView& v, const MiddleView& m, uint64_t bit_off
   if (v.bhiksha) {
     // ArrayBhiksha::ReadNext: last offset <= index, and last offset <= index + 1.
     const uint8_t* offs = v.blob + m.offsets_off;
-    uint64_t lo = 0, hi = m.offsets_count;  // upper_bound(index)
-    while (lo < hi) {
-      uint64_t mid = (lo + hi) >> 1;
-      if (load_u64(offs + mid * 8) <= index) lo = mid + 1;
-      else hi = mid;
+    // upper_bound(index).  offsets[k] is the first record whose next pointer has high part k, and next pointers grow
+    // about linearly with the record index, so an interpolated guess lands within a probe or two (every probe is a
+    // dependent memory access; bisection over <= 256 offsets cost 8 of them per n-gram level).
+    uint64_t lo = 0, hi = m.offsets_count;
+    uint64_t vlo = 0, vhi = m.n_records + 1;
+    for (int it = 0; lo < hi; ++it) {
+      uint64_t est;
+      if (it < 6 && vhi > vlo) est = lo + ((index >= vlo ? index - vlo : 0) * (hi - lo)) / (vhi - vlo + 1);
+      else est = lo + ((hi - lo) >> 1);
+      if (est >= hi) est = hi - 1;
+      const uint64_t x = load_u64(offs + est * 8);
+      if (x <= index) { lo = est + 1; vlo = x; }
+      else { hi = est; vhi = x; }
     }
     uint64_t begin_it = lo - 1;
     uint64_t end_it = begin_it + 1;
