@@ -1022,7 +1022,6 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
     lp.B = B; lp.T = T; lp.n_cell = Cp; lp.xw = b->d_xw; lp.h_all = b->d_hall; lp.c_state = b->d_c; lp.h_state = b->d_h;
     lp.barrier = b->d_barrier;
     lp.prof = b->d_lstm_prof;
-    lp.debug = getenv("STT_B200_LSTM_DEBUG") ? 1 : 0;
     const int grid = Cp / sttlstm::kCellsPerCta;
     if (launch_lstm(b, lp, grid, B, st)) return -1;
   }

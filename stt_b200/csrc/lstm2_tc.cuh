@@ -13,8 +13,6 @@
 //   the leader (rank 0) issues tcgen05.mma.cta_group::2 (M=256, N=128, K=16); D row i lives in TMEM lane i%128 of
 //   CTA i/128, columns 0..127, so each CTA's epilogue handles its own 128 utterances x 32 cells.
 #pragma once
-#include <cstdio>
-
 #include "lstm_tc.cuh"
 
 namespace sttlstm {
@@ -103,8 +101,6 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-#define DBG(...) do { if (p.debug && blockIdx.x < 2) printf(__VA_ARGS__); } while (0)
-  if (threadIdx.x == 0) DBG("[cta %d rank %u] start tmem_base=%u\n", blockIdx.x, crank, tmem_base);
 
   if (warp_idx == 0) {
     // ===================== TMA producer (+ grid-barrier waiter), one per CTA =====================
@@ -143,7 +139,6 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
             tma_load_2d_pair(sa + L::kABytes, &tmap_wh, leader_full, kb * BLOCK_K, n0 + (int)crank * (kPairN / 2));
           }
           tma_load_2d_pair(sa, &tmap_h, leader_full, kb * BLOCK_K, t * p.B + (int)crank * BLOCK_M);
-          if (kb == 0) DBG("[cta %d] producer t=%d issued kb0 (leader_full=%x local=%x)\n", blockIdx.x, t, leader_full, ptx::smem_u32(&full_bar[stage]));
           if (++stage == kPairStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -160,7 +155,6 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
       for (int t = 0; t < p.T; ++t) {
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
-          if (kb == 0 && lane == 0) DBG("[cta %d] mma t=%d passed full kb0\n", blockIdx.x, t);
           if (kb == 0) m0 = clock64();
           ptx::tc_fence_after();
           if (lane == 0) {
@@ -207,7 +201,6 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         }
       }
       ptx::mbar_wait(tmem_full_bar, t & 1);
-      if (threadIdx.x == 64) DBG("[cta %d] epilogue t=%d passed tmem_full\n", blockIdx.x, t);
       const long long e0 = clock64();
       ptx::tc_fence_after();
       float h_last[16];

@@ -44,7 +44,6 @@ struct LstmParams {
   float* c_state;        // [B, n_cell] fp32 in/out
   float* h_state;        // [B, n_cell] fp32 out (final h, full precision)
   unsigned int* barrier; // zero-initialised counter
-  int debug;             // device printf tracing (bring-up only)
   unsigned long long* prof; // [gridDim.x * 4] instrumentation (cycles): grid-barrier wait, load+MMA span, epilogue, -
 };
 
