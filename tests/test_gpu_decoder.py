@@ -192,3 +192,32 @@ def test_decoder_against_committed_golden(small_model):
         assert list(tok) == list(g["tokens"][u])
         assert list(ts) == list(g["timesteps"][u])
         assert conf == float(g["confidence"][u])
+
+
+@pytest.mark.parametrize("layout", ["trie", "quant_trie", "array_trie", "quant_array_trie"])
+def test_decoder_with_every_kenlm_trie_layout(ref_decoder, small_model, english, layout):
+    """Order-5 scorers in the four trie layouts (tests/golden/make_lm_variants.py, from kenlm's lm/test.arpa): the GPU
+    decoder -- word ordinals, carried KenLM states, interpolation searches, Bhiksha next pointers -- against the
+    reference decoder with the same package."""
+    import os
+    from conftest import GOLDEN
+    from stt_b200 import Model, synth
+    o = ref_decoder
+    pkg = os.path.join(GOLDEN, "lm_variants", layout + ".scorer")
+    vocab = [w for w in open(os.path.join(GOLDEN, "lm_variants", "vocab.txt")).read().split()
+             if all(c in english and c != " " for c in w)]
+    alpha = o.RefAlphabet(english)
+    sc = o.RefScorer(pkg, alpha)
+    path, _ = small_model
+    m = Model(path)
+    m.setBeamWidth(128)
+    m.enableExternalScorer(pkg)
+    B, T = 4, 120
+    probs = np.stack([synth.make_ctc_probs(vocab, T, utt=4242 + u) for u in range(B)])
+    b = m.createBatch(B, T * 320)
+    b.set_probs(probs, [T] * B)
+    b.decode(num_results=3)
+    b.fetch()
+    for u in range(B):
+        ref = o.ref_decode(probs[u], alpha, 128, sc, num_results=3)
+        _compare(b.results(u), ref, "layout=%s utt=%d" % (layout, u))
