@@ -65,3 +65,45 @@ def test_product_never_touches_the_oracle():
                     f in ("synth.py",), "%s mentions oracle/" % f
     assert "import oracle" not in open(os.path.join(pkg, "synth.py")).read()
     assert "from oracle" not in open(os.path.join(pkg, "synth.py")).read()
+
+
+REF_HEADER_DIR = "/root/reference/native_client"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_HEADER_DIR, "coqui-stt.h")), reason="reference tree not mounted")
+def test_client_built_against_the_reference_header_links_and_runs(tmp_path):
+    """Drop-in at the source level: a C client that includes the REFERENCE's coqui-stt.h compiles, links against
+    libstt_b200.so with every one of the 29 entry points resolved, and sees the reference's struct layouts."""
+    from stt_b200 import api
+    exe = str(tmp_path / "ref_client")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", REF_HEADER_DIR,
+                           os.path.join(ROOT, "tests", "native", "ref_header_client.c"), "-o", exe,
+                           "-L", os.path.dirname(api.lib_path()), "-lstt_b200",
+                           "-Wl,-rpath," + os.path.dirname(api.lib_path())])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = dict(l.split(" ", 1) for l in out.stdout.strip().splitlines())
+    assert lines["TokenMetadata"] == "16 8 12" and lines["CandidateTranscript"] == "24 8 16"
+    assert lines["AcousticModelEmissions"] == "32 8 16 24" and lines["Metadata"] == "24 8 16"
+    assert lines["version"].startswith("1.4.0") and lines["err"] == "Invalid scorer file."
+    assert lines["create_empty"] == "0x1000 1"          # STT_ERR_NO_MODEL, no model created
+    assert lines["resolved"] == "29"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_HEADER_DIR, "coqui-stt.h")), reason="reference tree not mounted")
+def test_our_header_declares_the_reference_prototypes_verbatim():
+    """Every STT_* prototype in include/stt_capi.h must be token-for-token the one in the reference header."""
+    def protos(path):
+        txt = re.sub(r"/\*.*?\*/", " ", open(path).read(), flags=re.S)
+        txt = re.sub(r"//[^\n]*", " ", txt)
+        out = {}
+        for m in re.finditer(r"STT_EXPORT\s+([^;{]*?\b(STT_[A-Za-z]+)\s*\([^;]*?\))\s*;", txt, flags=re.S):
+            out[m.group(2)] = re.sub(r"\s+", " ", m.group(1)).replace("( ", "(").replace(" )", ")").strip()
+        return out
+    ref = protos(os.path.join(REF_HEADER_DIR, "coqui-stt.h"))
+    ours = protos(os.path.join(ROOT, "include", "stt_capi.h"))
+    assert len(ref) == 29
+    for name, proto in ref.items():
+        assert name in ours, name
+        norm = lambda t: t.replace(" ", "").replace("(void)", "()")   # `f(void)` and `f()` declare the same C++ function
+        assert norm(ours[name]) == norm(proto), (name, ours[name], proto)
