@@ -107,3 +107,20 @@ def test_our_header_declares_the_reference_prototypes_verbatim():
         assert name in ours, name
         norm = lambda t: t.replace(" ", "").replace("(void)", "()")   # `f(void)` and `f()` declare the same C++ function
         assert norm(ours[name]) == norm(proto), (name, ours[name], proto)
+
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_stt_cli")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/ref_stt_cli not built (make -C oracle ref)")
+def test_reference_cli_runs_on_our_library(small_model):
+    """The reference's OWN client.cc (compiled unmodified, -DNO_SOX) linked against libstt_b200.so: `--version` goes
+    through our STT_Version, and without a GPU model creation fails the way client.cc reports it."""
+    from stt_b200 import api
+    out = subprocess.run([REF_CLI, "--version"], capture_output=True, text=True, timeout=60)
+    assert out.stdout.strip() == "Coqui " + api.version()   # (client.cc exits 1 after printing the version)
+    if not _have_gpu():
+        path, _ = small_model
+        r = subprocess.run([REF_CLI, "--model", path, "--audio", os.path.join(ROOT, "tests", "golden", "LDC93S1_pcms16le_1_16000.wav")],
+                           capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and "Could not create model" in r.stderr

@@ -77,3 +77,25 @@ def test_cli_on_the_reference_smoke_test_wav(small_model):
     m.enableExternalScorer(SCORER)
     base = ["--model", path, "--scorer", SCORER, "--audio", LDC93S1_WAV, "--beam_width", "64"]
     assert _run(*base)[0].strip().split("\n")[-1] == m.stt(pcm)
+
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_stt_cli")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/ref_stt_cli not built (make -C oracle ref)")
+def test_the_reference_cli_binary_transcribes_through_our_library(small_model):
+    """Drop-in, literally: native_client/client.cc compiled UNMODIFIED (-DNO_SOX) and linked against libstt_b200.so
+    transcribes the reference's smoke-test WAV; its output equals the library's own answer."""
+    from conftest import LDC93S1_WAV
+    from stt_b200 import Model
+    import wave
+    path, _ = small_model
+    with wave.open(LDC93S1_WAV, "rb") as w:
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+    m = Model(path)
+    m.setBeamWidth(64)
+    m.enableExternalScorer(SCORER)
+    r = subprocess.run([REF_CLI, "--model", path, "--scorer", SCORER, "--audio", LDC93S1_WAV, "--beam_width", "64"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip().split("\n")[-1] == m.stt(pcm)
