@@ -11,8 +11,10 @@ hot path (MFCC -> dense x3 -> LSTM -> dense x2 + softmax -> CTC beam search + Ke
 
 `value`   : whole-job RTFx with the PCM already resident in HBM, timed with CUDA events on the library's stream
             (sum of the per-stage event intervals; the stream is serial), max over ranks.
-`e2e`     : the same metric through the reference-facing C ABI with HOST buffers: pinned-host staging + H2D copy of the
-            int16 PCM, the device pipeline, D2H copy of tokens/timesteps/confidence and transcript assembly, wall clock.
+`e2e`     : the same metric through the reference-facing C ABI with HOST buffers: H2D copy of every step's PCM from
+            pinned host memory + device pipeline + D2H of the results, wall clock.  Two staged batch contexts are kept in
+            flight (stt_b200.BatchPipeline), so one batch's copy and host work overlap the other's kernels; every step
+            still uploads its own PCM and fetches its own results.
 `roofline`: dominant kernel of the step against MEASURED_PEAKS.json.
 `cpu_baseline` (rank 0, N=1): restated acoustic model (torch CPU fp32, all host threads, TFLite is not buildable
             offline) + the GENUINE reference decoder (ctc_beam_search_decoder_batch, all host cores) on a bounded
