@@ -148,3 +148,48 @@ def test_cli_tool_on_a_fresh_lm(tmp_path, ref_decoder, english):
     assert sc.log_cond_prob(["looking", "on"], True) < 0.0
     with pytest.raises(ValueError):
         sp.create_scorer_package(pkg, ["a"], english, str(tmp_path / "again.scorer"), 0.9, 1.2)   # already packaged
+
+
+def test_dictionary_is_exact_and_minimal_on_random_vocabularies(english):
+    """build_dictionary accepts exactly {word + space}; no two states are equivalent (minimality) and every state is
+    reachable and co-reachable -- on random vocabularies with shared prefixes and suffixes."""
+    from stt_b200 import scorer_package as sp
+    rng = np.random.default_rng(20260922)
+    letters = [l for l in english if l != " "]
+    lab = {l: i + 1 for i, l in enumerate(english)}
+    for trial in range(20):
+        stems = ["".join(rng.choice(letters[:6], size=int(rng.integers(1, 5)))) for _ in range(8)]
+        sufs = ["", "s", "ing", "ed", "er"]
+        words = sorted({s + sufs[int(rng.integers(len(sufs)))] for s in stems for _ in range(3)})
+        start, fin, arcs, n = sp.build_dictionary(words + ["<s>", "</s>", "<unk>", "café"], english)   # skipped entries
+        assert n == len(words) and start == 0
+
+        def accepts(w):
+            s = 0
+            for ch in w + " ":
+                nxt = dict(arcs[s]).get(lab[ch])
+                if nxt is None:
+                    return False
+                s = nxt
+            return fin[s]
+        for w in words:
+            assert accepts(w)
+        for w in {w[:-1] for w in words if len(w) > 1} | {w + "x" for w in words}:
+            assert accepts(w) == (w in words)
+        # arcs sorted by label, deterministic; finals have no outgoing arcs (every word ends with the space)
+        for s, row in enumerate(arcs):
+            assert [l for l, _ in row] == sorted({l for l, _ in row})
+            assert not (fin[s] and row)
+        # minimal: the right languages of distinct states differ <=> signatures (finality, arcs to classes) are unique
+        sigs = {(fin[s], tuple(row)) for s, row in enumerate(arcs)}
+        assert len(sigs) == len(arcs)
+        # accessible by construction (BFS numbering); co-accessible: every state reaches a final state
+        good = {s for s in range(len(arcs)) if fin[s]}
+        changed = True
+        while changed:
+            changed = False
+            for s, row in enumerate(arcs):
+                if s not in good and any(nx in good for _, nx in row):
+                    good.add(s)
+                    changed = True
+        assert len(good) == len(arcs)
