@@ -52,6 +52,10 @@ def port():
         L.orc_mfcc_compute.argtypes = [c_void_p, c_void_p, c_void_p]
         L.orc_spectrogram_frame.argtypes = [c_void_p, c_int, c_int, c_void_p]
         L.orc_am_infer.argtypes = [POINTER(_OrcAm), c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+        L.orc_am_quantize.restype = c_void_p
+        L.orc_am_quantize.argtypes = [POINTER(_OrcAm)]
+        L.orc_am_q_free.argtypes = [c_void_p]
+        L.orc_am_infer_hybrid.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
         L.orc_stream_new.restype = c_void_p
         L.orc_stream_new.argtypes = [POINTER(_OrcAm), c_int, c_int, c_int, c_int]
         L.orc_stream_free.argtypes = [c_void_p]
@@ -101,6 +105,34 @@ class PortAM(object):
                          *[self.w[k].ctypes.data for k in ("w1", "b1", "w2", "b2", "w3", "b3", "lstm_kernel",
                                                           "lstm_bias", "w5", "b5", "w6", "b6")])
         self.n_classes, self.n_input = K, n_input
+
+    def forward_features(self, mfcc, mode="fp32", n_steps=16):
+        """mfcc [F, n_input] -> probs [F, K], `n_steps` timesteps per infer call with carried LSTM state, zero-padded last
+        call (tflitemodelstate.cc:369-405).  mode "hybrid8" = TFLite hybrid int8 arithmetic (orc_am_infer_hybrid)."""
+        L = port()
+        F = mfcc.shape[0]
+        nc, ni = self.am.n_context, self.n_input
+        pad = np.zeros((nc, ni), np.float32)
+        seq = np.concatenate([pad, np.asarray(mfcc, np.float32), pad])
+        win = np.stack([seq[t:t + 2 * nc + 1].reshape(-1) for t in range(F)]) if F else np.zeros((0, (2 * nc + 1) * ni), np.float32)
+        C = self.am.n_cell
+        c = np.zeros(C, np.float32)
+        h = np.zeros(C, np.float32)
+        out = np.zeros((F, self.n_classes), np.float32)
+        q = L.orc_am_quantize(byref(self.am)) if mode == "hybrid8" else None
+        for t0 in range(0, F, n_steps):
+            x = np.zeros((n_steps, win.shape[1]), np.float32)
+            n = min(n_steps, F - t0)
+            x[:n] = win[t0:t0 + n]
+            p = np.zeros((n_steps, self.n_classes), np.float32)
+            if q:
+                L.orc_am_infer_hybrid(q, x.ctypes.data, n_steps, c.ctypes.data, h.ctypes.data, p.ctypes.data)
+            else:
+                L.orc_am_infer(byref(self.am), x.ctypes.data, n_steps, c.ctypes.data, h.ctypes.data, p.ctypes.data)
+            out[t0:t0 + n] = p[:n]
+        if q:
+            L.orc_am_q_free(q)
+        return out
 
     def stream(self, pcm, sample_rate=16000, win_len=512, win_step=320, n_steps=16, chunks=None, flush_at=()):
         """Run the restated streaming runtime.  chunks: list of chunk sizes (default: everything at once);

@@ -189,6 +189,105 @@ void orc_am_infer(const orc_am* am, const float* x, int n_steps, float* c, float
   free(a); free(b); free(xh); free(gates); free(logits);
 }
 
+/* ------------------------------------------------------------------ hybrid int8 mode
+ * What a DEFAULT Coqui export computes (config.py:616-622 export_quantize -> export.py:145-146 Optimize.DEFAULT):
+ * TFLite "hybrid" FULLY_CONNECTED, tensorflow/lite/kernels/fully_connected.cc:435-503 (EvalHybridDense):
+ *   weights: per-tensor symmetric int8, scale = max|w|/127 (quantize_weights);
+ *   input row: PortableSymmetricQuantizeFloats (internal/reference/portable_tensor_utils.cc:51-70): scale = max|x|/127,
+ *              q = TfLiteRound(x * 127/max|x|) (round half away from zero), clamped to +-127;
+ *   output = bias; all-zero input rows skip the matmul (:455-461);
+ *   result += (float)int32_dot * (input_scale * weight_scale)  (:138-161).
+ * The LSTM's matmul quantises concat([x_t, h]) as ONE row (rnn_cell_impl.py:1060). */
+static float tfl_round(float x) { return roundf(x); } /* TfLiteRound == std::round: half away from zero */
+
+void orc_quantize_weights(const float* w, size_t n, int8_t* q, float* scale) {
+  float range = 0.0f;
+  for (size_t i = 0; i < n; ++i) { const float a = fabsf(w[i]); if (a > range) range = a; }
+  if (range == 0.0f) { memset(q, 0, n); *scale = 1.0f; return; }
+  *scale = range / 127.0f;
+  const float inv = 127.0f / range;
+  for (size_t i = 0; i < n; ++i) {
+    int v = (int)tfl_round(w[i] * inv);
+    q[i] = (int8_t)(v > 127 ? 127 : (v < -127 ? -127 : v));
+  }
+}
+
+/* y[n_out] = b + hybrid(x[n_in] @ Wq[n_in, n_out]) */
+static void hybrid_row(const float* x, const int8_t* wq, float wscale, const float* b, int n_in, int n_out, float* y,
+                       int8_t* xq, int32_t* acc) {
+  for (int j = 0; j < n_out; ++j) y[j] = b[j];
+  float range = 0.0f;
+  for (int i = 0; i < n_in; ++i) { const float a = fabsf(x[i]); if (a > range) range = a; }
+  if (range == 0.0f) return; /* IsZeroVector shortcut */
+  const float sf = range / 127.0f, inv = 127.0f / range;
+  for (int i = 0; i < n_in; ++i) {
+    int v = (int)tfl_round(x[i] * inv);
+    xq[i] = (int8_t)(v > 127 ? 127 : (v < -127 ? -127 : v));
+  }
+  memset(acc, 0, sizeof(int32_t) * n_out);
+  for (int i = 0; i < n_in; ++i) {
+    const int32_t xi = xq[i];
+    if (!xi) continue;
+    const int8_t* wr = wq + (size_t)i * n_out;
+    for (int j = 0; j < n_out; ++j) acc[j] += xi * wr[j];
+  }
+  const float scale = sf * wscale;
+  for (int j = 0; j < n_out; ++j) y[j] += (float)acc[j] * scale;
+}
+
+void orc_am_infer_hybrid(const orc_am_q* q, const float* x, int n_steps, float* c, float* h, float* probs) {
+  const orc_am* am = q->am;
+  const int n_in = (2 * am->n_context + 1) * am->n_input;
+  const int H = am->n_hidden, C = am->n_cell, K = am->n_classes;
+  const int widest = 4 * C > H ? 4 * C : H;
+  float* a = (float*)malloc(sizeof(float) * H);
+  float* b = (float*)malloc(sizeof(float) * H);
+  float* xh = (float*)malloc(sizeof(float) * (H + C));
+  float* gates = (float*)malloc(sizeof(float) * 4 * C);
+  float* logits = (float*)malloc(sizeof(float) * K);
+  int8_t* xq = (int8_t*)malloc((size_t)(H + C > n_in ? H + C : n_in));
+  int32_t* acc = (int32_t*)malloc(sizeof(int32_t) * widest);
+  for (int t = 0; t < n_steps; ++t) {
+    hybrid_row(x + (size_t)t * n_in, q->w1, q->s1, am->b1, n_in, H, a, xq, acc); clipped_relu(a, H, am->relu_clip);
+    hybrid_row(a, q->w2, q->s2, am->b2, H, H, b, xq, acc); clipped_relu(b, H, am->relu_clip);
+    hybrid_row(b, q->w3, q->s3, am->b3, H, H, a, xq, acc); clipped_relu(a, H, am->relu_clip);
+    memcpy(xh, a, sizeof(float) * H);
+    memcpy(xh + H, h, sizeof(float) * C);
+    hybrid_row(xh, q->lstm_kernel, q->sk, am->lstm_bias, H + C, 4 * C, gates, xq, acc);
+    for (int j = 0; j < C; ++j) {
+      const float gi = gates[j], gj = gates[C + j], gf = gates[2 * C + j], go = gates[3 * C + j];
+      const float cn = sigmoidf_(gf) * c[j] + sigmoidf_(gi) * tanhf(gj);
+      c[j] = cn;
+      h[j] = sigmoidf_(go) * tanhf(cn);
+    }
+    hybrid_row(h, q->w5, q->s5, am->b5, C, H, a, xq, acc); clipped_relu(a, H, am->relu_clip);
+    hybrid_row(a, q->w6, q->s6, am->b6, H, K, logits, xq, acc);
+    float mx = logits[0];
+    for (int j = 1; j < K; ++j) if (logits[j] > mx) mx = logits[j];
+    float sum = 0.0f;
+    for (int j = 0; j < K; ++j) { logits[j] = expf(logits[j] - mx); sum += logits[j]; }
+    for (int j = 0; j < K; ++j) probs[(size_t)t * K + j] = logits[j] / sum;
+  }
+  free(a); free(b); free(xh); free(gates); free(logits); free(xq); free(acc);
+}
+
+orc_am_q* orc_am_quantize(const orc_am* am) {
+  orc_am_q* q = (orc_am_q*)calloc(1, sizeof(orc_am_q));
+  const size_t n_in = (size_t)(2 * am->n_context + 1) * am->n_input, H = am->n_hidden, C = am->n_cell, K = am->n_classes;
+  q->am = am;
+  q->w1 = (int8_t*)malloc(n_in * H); orc_quantize_weights(am->w1, n_in * H, q->w1, &q->s1);
+  q->w2 = (int8_t*)malloc(H * H); orc_quantize_weights(am->w2, H * H, q->w2, &q->s2);
+  q->w3 = (int8_t*)malloc(H * H); orc_quantize_weights(am->w3, H * H, q->w3, &q->s3);
+  q->lstm_kernel = (int8_t*)malloc((H + C) * 4 * C); orc_quantize_weights(am->lstm_kernel, (H + C) * 4 * C, q->lstm_kernel, &q->sk);
+  q->w5 = (int8_t*)malloc(C * H); orc_quantize_weights(am->w5, C * H, q->w5, &q->s5);
+  q->w6 = (int8_t*)malloc(H * K); orc_quantize_weights(am->w6, H * K, q->w6, &q->s6);
+  return q;
+}
+void orc_am_q_free(orc_am_q* q) {
+  if (!q) return;
+  free(q->w1); free(q->w2); free(q->w3); free(q->lstm_kernel); free(q->w5); free(q->w6); free(q);
+}
+
 /* ------------------------------------------------------------------ streaming runtime */
 typedef struct { float* d; size_t n, cap; } fvec;
 static void fv_push(fvec* v, const float* src, size_t n) {

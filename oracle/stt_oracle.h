@@ -15,6 +15,7 @@
  */
 #ifndef STT_ORACLE_H
 #define STT_ORACLE_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -51,6 +52,19 @@ typedef struct {
 /* One `infer` call (tflitemodelstate.cc:369-405): x is [n_steps, (2*n_context+1)*n_input],
  * c/h [n_cell] are updated in place, probs [n_steps, n_classes]. */
 void orc_am_infer(const orc_am* am, const float* x, int n_steps, float* c, float* h, float* probs);
+
+/* ---- hybrid int8 mode (the reference's DEFAULT export arithmetic): TFLite EvalHybridDense,
+ *      tensorflow/lite/kernels/fully_connected.cc:435-503 + internal/reference/portable_tensor_utils.cc:51-70,138-161.
+ *      Weights are int8 per-tensor symmetric in the same [in, out] layout. */
+typedef struct {
+  const orc_am* am; /* geometry + fp32 biases */
+  int8_t *w1, *w2, *w3, *lstm_kernel, *w5, *w6;
+  float s1, s2, s3, sk, s5, s6; /* weight scales */
+} orc_am_q;
+void orc_quantize_weights(const float* w, size_t n, int8_t* q, float* scale);
+orc_am_q* orc_am_quantize(const orc_am* am);
+void orc_am_q_free(orc_am_q* q);
+void orc_am_infer_hybrid(const orc_am_q* q, const float* x, int n_steps, float* c, float* h, float* probs);
 
 /* ---- streaming runtime: native_client/stt.cc:105-128 (feedAudioContent), :226-334
  *      (processAudioWindow, flushBuffers, pushMfccBuffer, processMfccWindow, processBatch),
