@@ -171,6 +171,9 @@ STT_EXPORT int STTX_BatchTokens(STTX_Batch* b, unsigned int u, unsigned int r, u
 STT_EXPORT int STTX_BatchFetch(STTX_Batch* b);                         /* device -> host copy of the decode results */
 STT_EXPORT int STTX_BatchGetTimings(STTX_Batch* b, STTX_Timings* out);
 STT_EXPORT long long STTX_BatchKernelLaunches(STTX_Batch* b);
+/* statistics build of the decoder kernel (per-phase clocks, LM counters) for the following STTX_BatchDecode calls;
+ * off by default: the production kernel carries no instrumentation */
+STT_EXPORT int STTX_BatchSetInstrumented(STTX_Batch* b, int aOn);
 /* instrumentation: words scored by the LM / LM calls in the last STTX_BatchDecode (decoder roofline's Q) */
 /* instrumentation: SM cycles per decoder phase (gate, child discovery, LM, live update, children, select, commit, -),
  * summed over the batch's utterances, for the last STTX_BatchDecode */

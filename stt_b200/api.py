@@ -54,7 +54,7 @@ DECLARED_SYMBOLS = [
     "STT_ErrorCodeToErrorMessage",
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
-    "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
+    "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchSetInstrumented", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
     "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout",
 ]
 
@@ -125,6 +125,7 @@ def lib():
     L.STTX_BatchTokens.argtypes = [vp, c_uint, c_uint, c_void_p, c_void_p, c_uint, POINTER(c_double)]
     L.STTX_BatchGetTimings.argtypes = [vp, POINTER(_Timings)]
     L.STTX_BatchKernelLaunches.argtypes = [vp]
+    L.STTX_BatchSetInstrumented.argtypes = [vp, c_int]
     L.STTX_BatchKernelLaunches.restype = c_longlong
     L.STTX_BatchTimesteps.argtypes = [vp, c_uint]
     L.STTX_BatchPhaseCycles.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
@@ -429,6 +430,10 @@ class Batch(object):
 
     def kernel_launches(self):
         return lib().STTX_BatchKernelLaunches(self._impl)
+
+    def set_instrumented(self, on=True):
+        """Following decode() calls run the statistics build of the decoder kernel (phase_cycles / lm_stats)."""
+        lib().STTX_BatchSetInstrumented(self._impl, 1 if on else 0)
 
     def timesteps(self, u):
         return lib().STTX_BatchTimesteps(self._impl, u)

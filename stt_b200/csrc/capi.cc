@@ -26,6 +26,10 @@ struct ModelState {  // native_client/modelstate.h:13-27
   std::map<std::string, float> hot_words_;
   std::vector<stteng::Batch*> stream_pool;  // idle single-stream device contexts
   bool warned_hot_words = false;
+  // device context of the last STTX_SpeechToTextBatch call, kept while the next call fits in it (a context for 256 x 10 s
+  // is ~13 GB of device buffers: allocating it per call would cost more than the transcription)
+  struct STTX_Batch* oneshot = nullptr;
+  unsigned int oneshot_utts = 0, oneshot_samples = 0;
 };
 
 struct StreamingState {  // native_client/stt.cc:60-95
@@ -335,6 +339,7 @@ int STT_GetModelSampleRate(const ModelState* aCtx) { return (int)stteng::engine_
 void STT_FreeModel(ModelState* ctx) {
   if (!ctx) return;
   for (stteng::Batch* b : ctx->stream_pool) stteng::batch_destroy(b);
+  if (ctx->oneshot) STTX_BatchFree(ctx->oneshot);
   stteng::engine_destroy(ctx->engine);
   delete ctx;
 }
@@ -563,6 +568,10 @@ int STTX_BatchGetTimings(STTX_Batch* b, STTX_Timings* out) {
   return STT_ERR_OK;
 }
 long long STTX_BatchKernelLaunches(STTX_Batch* b) { return stteng::batch_kernel_launches(b->dev); }
+int STTX_BatchSetInstrumented(STTX_Batch* b, int aOn) {
+  stteng::batch_set_instrumented(b->dev, aOn != 0);
+  return STT_ERR_OK;
+}
 int STTX_BatchPhaseCycles(STTX_Batch* b, unsigned long long* out8) {
   return stteng::batch_phase_cycles(b->dev, out8) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
 }
@@ -603,9 +612,17 @@ int STTX_SpeechToTextBatch(ModelState* aCtx, const short* const* aBuffers, const
   unsigned int max_samples = 1;
   for (unsigned int i = 0; i < aNumBuffers; ++i) max_samples = std::max(max_samples, aBufferSizes[i]);
   const unsigned int group = std::min(256u, std::max(1u, aNumBuffers));
-  STTX_Batch* b = nullptr;
-  int err = STTX_BatchCreate(aCtx, group, max_samples, &b);
-  if (err) return err;
+  STTX_Batch* b = aCtx->oneshot;
+  int err = STT_ERR_OK;
+  if (!b || aCtx->oneshot_utts < group || aCtx->oneshot_samples < max_samples || b->beam_cap < std::max(1u, aCtx->beam_width_)) {
+    if (b) STTX_BatchFree(b);
+    aCtx->oneshot = nullptr;
+    err = STTX_BatchCreate(aCtx, group, max_samples, &b);
+    if (err) return err;
+    aCtx->oneshot = b;
+    aCtx->oneshot_utts = group;
+    aCtx->oneshot_samples = max_samples;
+  }
   for (unsigned int base = 0; base < aNumBuffers && !err; base += group) {
     const unsigned int n = std::min(group, aNumBuffers - base);
     err = STTX_BatchUpload(b, aBuffers + base, aBufferSizes + base, n);
@@ -614,7 +631,6 @@ int STTX_SpeechToTextBatch(ModelState* aCtx, const short* const* aBuffers, const
     if (!err) err = STTX_BatchFetch(b);
     for (unsigned int i = 0; i < n && !err; ++i) aTranscriptsOut[base + i] = STTX_BatchTranscript(b, i, 0);
   }
-  STTX_BatchFree(b);
   return err;
 }
 

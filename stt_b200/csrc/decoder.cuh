@@ -43,6 +43,13 @@ constexpr int kMaxWordBytes = 128;
 constexpr int kStateWords = sttscorer::kMaxOrder - 1;
 constexpr int kMaxHotWords = 32;
 constexpr int kCommitRounds = 8;   // candidate rounds (of NT) compacted per scan in phase 6
+constexpr int kHelperWarps = 2;    // LM helper warps of the step kernel (decoder_step_kernel), when it has any
+constexpr int kSelBins = 2048;     // phase 5: bins of the one-pass score histogram
+constexpr int kSelBoundaryCap = 256;  // phase 5: boundary-bin elements resolved by pairwise ranking (more: radix passes)
+// "not computed" marker of Slot::lm_cond (a quiet NaN no LM result can equal): the 8-byte conditional probability is the
+// cache's valid flag AND its payload, so a reader needs no ordering between two loads
+constexpr unsigned long long kLmUnset = 0x7ff8dead5117b200ull;
+constexpr int kFlagHistSelect = 1, kFlagLmHelper = 2;   // DecodeParams::flags
 
 struct Node {            // one surviving prefix (PathTrie node), 32 bytes
   uint32_t parent;       // arena id, kNone for the root
@@ -114,6 +121,7 @@ struct DecodeParams {
   const uint32_t* fst_space_skip;  // [n_states] skip of the state's space arc when that arc ends a word, else kNone
   const uint32_t* ord2wid;         // [n_words] KenLM vocabulary id (0 = <unk>)
   // hot words (ctc_beam_search_decoder.cpp:224-236): vocabulary ids and boosts, snapshotted when the stream starts
+  int flags;             // kFlagHistSelect | kFlagLmHelper
   int n_hot;
   uint32_t hot_id[kMaxHotWords];
   float hot_boost[kMaxHotWords];
@@ -246,19 +254,29 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
                                uint32_t* n_window_out) {
   const sttscorer::ScorerView& v = p.scorer;
   const int order = (int)v.order;
-  const uint32_t meta0 = s.lm_meta[node];   // kNone = not computed yet (space nodes: the carried context, see above)
-  const double cond0 = s.lm_cond[node];
-  const Node nd = s.nodes[node];
+  // Loads go to L2 (__ldcg): the step kernel's helper warps fill these arrays concurrently (same SM, but an L1 line
+  // fetched earlier must not be believed).  lm_cond is written LAST by whoever evaluates a node, so "cond is set" implies
+  // that the node's state words and meta are in place.
+  const unsigned long long c0bits = __ldcg(reinterpret_cast<const unsigned long long*>(&s.lm_cond[node]));
+  const uint32_t meta0 = __ldcg(&s.lm_meta[node]);   // space nodes: the carried context, see above
+  const double cond0 = __longlong_as_double((long long)c0bits);
+  Node nd;
+  {
+    const uint4* np = reinterpret_cast<const uint4*>(&s.nodes[node]);
+    const uint4 n0 = __ldcg(np), n1 = __ldcg(np + 1);
+    nd.parent = n0.x; nd.chr = n0.y; nd.dict = (int32_t)n0.z; nd.last_space = n0.w;
+    nd.word_id = n1.x; nd.live_slot = n1.y; nd.lm_wid = n1.z; nd.child_mask = n1.w;
+  }
   uint32_t stop = stop_hint;
   uint32_t cmeta = kNone;
   uint32_t csw[kStateWords];
   float csb[kStateWords];
   if (stop_hint != kStopUnknown && stop_hint != kNone) {
-    cmeta = s.lm_meta[stop_hint];
+    cmeta = __ldcg(&s.lm_meta[stop_hint]);
 #pragma unroll
     for (int i = 0; i < kStateWords; ++i) {
-      csw[i] = s.lm_sw[(size_t)stop_hint * kStateWords + i];
-      csb[i] = s.lm_sb[(size_t)stop_hint * kStateWords + i];
+      csw[i] = __ldcg(&s.lm_sw[(size_t)stop_hint * kStateWords + i]);
+      csb[i] = __ldcg(&s.lm_sb[(size_t)stop_hint * kStateWords + i]);
     }
   }
   const uint32_t cc = nd.chr;
@@ -271,11 +289,11 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
   if (stop == kStopUnknown) {
     stop = nd.last_space;  // == node when node is itself a space (empty word)
     if (stop != kNone) {
-      cmeta = s.lm_meta[stop];
+      cmeta = __ldcg(&s.lm_meta[stop]);
 #pragma unroll
       for (int i = 0; i < kStateWords; ++i) {
-        csw[i] = s.lm_sw[(size_t)stop * kStateWords + i];
-        csb[i] = s.lm_sb[(size_t)stop * kStateWords + i];
+        csw[i] = __ldcg(&s.lm_sw[(size_t)stop * kStateWords + i]);
+        csb[i] = __ldcg(&s.lm_sb[(size_t)stop * kStateWords + i]);
       }
     }
   }
@@ -288,9 +306,9 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
     *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
     return -1000.0;
   }
-  if (meta0 != kNone) {
+  if (c0bits != kLmUnset) {
     *word_out = nd.lm_wid;
-    const uint32_t nw = meta0 >> 16;
+    const uint32_t nw = meta0 >> 16;   // statistics only (instrumented builds run without the helper warps)
     *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
     return cond0;
   }
@@ -357,8 +375,9 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
     s.lm_sb[(size_t)node * kStateWords + i] = out.backoff[i];
   }
   s.lm_meta[node] = meta;
-  s.lm_cond[node] = cond;
   if (nd.lm_wid == kNone) s.nodes[node].lm_wid = wid;
+  __threadfence_block();          // state, meta and word id first ...
+  __stcg(&s.lm_cond[node], cond); // ... then the value whose presence says "computed"
   *word_out = wid;
   const uint32_t nw = meta >> 16;
   *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
@@ -406,6 +425,7 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start,
   root.live_slot = 0; root.lm_wid = kNone; root.child_mask = 0;
   s.nodes[0] = root;
   s.lm_meta[0] = kNone;
+  reinterpret_cast<unsigned long long*>(s.lm_cond)[0] = kLmUnset;
   s.ht_gen = ht_gen;
   s.ts_tree[0] = make_uint2(kNone, 0u);
   s.score[0] = 0.f;
@@ -422,6 +442,11 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start,
 
 // ------------------------------------------------------------------------------------------------ step kernel
 // Block-wide exclusive scan of one count per thread; returns the thread's offset and the block total.
+// Barrier among the NT prefix threads of the step kernel (its helper warps never join): named barrier 1.
+template <int NT>
+__device__ __forceinline__ void main_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
 template <int NT, bool kTrailingBarrier = true>
 __device__ __forceinline__ uint32_t block_scan(uint32_t cnt, uint32_t* warp_sums /*[NT/32 + 1]*/, uint32_t& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -432,7 +457,7 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t cnt, uint32_t* warp_sums
     if (lane >= d) incl += o;
   }
   if (lane == 31) warp_sums[warp] = incl;
-  __syncthreads();
+  main_sync<NT>();
   if (warp == 0) {
     uint32_t v = (lane < NT / 32) ? warp_sums[lane] : 0, inc2 = v;
 #pragma unroll
@@ -443,10 +468,10 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t cnt, uint32_t* warp_sums
     if (lane < NT / 32) warp_sums[lane] = inc2 - v;
     if (lane == 31) warp_sums[NT / 32] = inc2;
   }
-  __syncthreads();
+  main_sync<NT>();
   const uint32_t off = warp_sums[warp] + (incl - cnt);
   total = warp_sums[NT / 32];
-  if (kTrailingBarrier) __syncthreads();  // callers that scan again before another barrier need warp_sums intact
+  if (kTrailingBarrier) main_sync<NT>();  // callers that scan again before another barrier need warp_sums intact
   return off;
 }
 
@@ -475,8 +500,13 @@ struct StepSmem {
   uint32_t p0[NC > 0 ? NC : 1], p1[NC > 0 ? NC : 1];
 };
 
-template <int NT, int WC, int NC>
-__global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
+// Launch with NT + 32 * HW threads: threads [0, NT) own the live prefixes; the last HW warps are LM helpers (see the
+// helper loop below).  kInstr compiles in the per-phase clocks and LM counters (bench statistics).  Two CTAs per SM for
+// beams <= 512 (the register budget follows from that), one for the wide instantiation.
+template <int NT, int WC, int NC, bool kInstr, int HW>
+__global__ void __launch_bounds__(NT + 32 * HW, (WC <= 512 ? 2 : 1))
+decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
+  constexpr int kHelperThreads = 32 * HW;
   static_assert(NT == 512, "phase 6 assumes 16 warps (kCommitRounds * 16 warp counts scanned by one warp)");
   __shared__ Slot s_slot;   // the slot's pointers and capacities are read all over the step loop
   const int tid = threadIdx.x;
@@ -499,9 +529,11 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
   __shared__ double s_nextp[kMaxClasses];   // next row of probabilities, fetched with cp.async (f32 rows use the first half)   // "a node was revived" flags of the last two commits
   __shared__ uint32_t s_cnt[kCommitRounds * (NT / 32) + 1];
   __shared__ uint32_t s_warp[NT / 32 + 1];
-  __shared__ float s_red[NT / 32];
+  __shared__ float s_red[NT / 32], s_red2[NT / 32];
   __shared__ uint32_t s_u[8];
   __shared__ unsigned long long s_ph[8];
+  __shared__ unsigned long long s_thresh;   // phase 5: smallest selected key of the boundary bin
+  __shared__ uint32_t s_help[2];            // [0] arena nodes published to the LM helper warps, [1] "launch finished"
   extern __shared__ __align__(16) uint8_t s_dyn[];
   StepSmem<WC, NC>& sm = *reinterpret_cast<StepSmem<WC, NC>*>(s_dyn);
 
@@ -516,6 +548,41 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     s_u[6] = 0;
     s_u[7] = 0;
     for (int q = 0; q < 8; ++q) s_ph[q] = 0;
+    s_help[0] = arena_count;
+    s_help[1] = 0;
+  }
+  __syncthreads();
+  // ---- LM helper warps.  A prefix's LM term is needed on the critical path the moment the prefix is extended by the
+  //      space label, and evaluating it is a chain of ~10 dependent L2/DRAM round trips (KenLM trie descent) that a
+  //      handful of the NT prefix threads would walk while all the others wait at the next barrier.  The term depends on
+  //      the NODE only, so these warps evaluate every newly created node that completes a dictionary word as soon as
+  //      the commit that created it has been published -- typically a full step before anybody asks -- and leave the
+  //      result in the per-node cache (Slot::lm_cond).  They never join the prefix threads' barrier; a prefix thread
+  //      that finds the cache empty simply evaluates inline as before, so results do not depend on helper timing.
+  if (HW > 0 && tid >= NT) {
+    if (!kInstr && p.has_scorer && p.fst_space_skip != nullptr) {
+      const uint32_t hl = (uint32_t)(tid - NT);
+      uint32_t base = arena_count;   // nodes created by earlier launches are left to the inline path
+      for (;;) {
+        const uint32_t pub = *reinterpret_cast<volatile uint32_t*>(&s_help[0]);
+        if (base < pub) {
+          __threadfence();
+          for (uint32_t id = base + hl; id < pub; id += (uint32_t)kHelperThreads) {
+            const uint4 n1 = __ldcg(reinterpret_cast<const uint4*>(&s.nodes[id]) + 1);   // {word_id|ord, live_slot, lm_wid, child_mask}
+            if (n1.z != kNone) {   // completes a word (set at creation): Scorer::get_log_cond_prob will be asked about it
+              uint32_t w_unused, n_unused;
+              lm_eval_node(s, p, id, kStopUnknown, &w_unused, &n_unused);
+            }
+          }
+          base = pub;
+        } else if (*reinterpret_cast<volatile uint32_t*>(&s_help[1])) {
+          break;
+        } else {
+          __nanosleep(200);
+        }
+      }
+    }
+    return;
   }
   uint32_t* const aux_base = (WC <= 512) ? sm.aux : s.aux;
   uint32_t* const aux_ord[2] = {aux_base, aux_base + WC};
@@ -576,9 +643,9 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       s_logblank[0] = log(pb);
     }
   }
-  __syncthreads();
-  long long ph_t0 = clock64();
-#define PHASE_MARK(k) do { if (tid == 0) { const long long _t = clock64(); s_ph[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
+  main_sync<NT>();
+  long long ph_t0 = kInstr ? clock64() : 0;
+#define PHASE_MARK(k) do { if (kInstr && tid == 0) { const long long _t = clock64(); s_ph[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
 
   for (int step = 0; step < in.n_steps; ++step, ++abs_t) {
     LiveList<WC>& L = sm.live[cur];
@@ -592,6 +659,13 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     //      into log-probs at the end of this step, off the critical path.
     const int cb = step & 1;
     const float* s_logp = s_logp2[cb];
+    // phase 5's score histogram lives in the NEXT live list's storage (dead until phase 6 writes it): clear it now, the
+    // barrier below publishes the zeros
+    uint32_t* const sel_hist = reinterpret_cast<uint32_t*>(&Nx);
+    unsigned long long* const sel_blist = reinterpret_cast<unsigned long long*>(sel_hist + kSelBins);
+    static_assert(kSelBins == 4 * NT, "one uint4 of histogram bins per prefix thread");
+    static_assert(sizeof(LiveList<WC>) >= kSelBins * 4 + kSelBoundaryCap * 8, "select scratch must fit in a live list");
+    reinterpret_cast<uint4*>(sel_hist)[tid] = make_uint4(0u, 0u, 0u, 0u);
     const bool have_next = (step + 1 < in.n_steps);
     if (have_next && tid < C) {
       // asynchronous copy straight into shared memory: a register destination would be spilled, and the spill store
@@ -642,11 +716,11 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       if ((tid & 31) == 0) s_red[tid >> 5] = m;
     }
     start_expanding |= s_gate[cb];
-    __syncthreads();
+    main_sync<NT>();
     PHASE_MARK(1);
     if (!start_expanding || overflow) {
       if (have_next && tid < C) next_row_ready(cb ^ 1);
-      __syncthreads();
+      main_sync<NT>();
       continue;
     }
     // min_cutoff (:134-146), computed redundantly by every thread to save a barrier
@@ -686,8 +760,10 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
               if (p.n_hot > 0) cond += (double)hot_word_boost(s, p, L.node[i], wid);
               sm.lmterm[i] = (float)(cond * sv.alpha);
               sm.lmwid[i] = wid;
-              atomicAdd(&s_u[6], nw);
-              atomicAdd(&s_u[7], 1u);
+              if (kInstr) {
+                atomicAdd(&s_u[6], nw);
+                atomicAdd(&s_u[7], 1u);
+              }
             }
             allow = L.mask[i] & all_labels & ~sm.child[i];
             if (full_beam) {
@@ -711,7 +787,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
       n_new = run_base;
     }
     const uint32_t N = n_live + n_new;
-    if (N > s.cand_cap) { overflow = 1; __syncthreads(); continue; }
+    if (N > s.cand_cap) { overflow = 1; main_sync<NT>(); continue; }
     max_cand = N > max_cand ? N : max_cand;
     const bool in_smem = (NC > 0) && (N <= (uint32_t)NC);
     if (!in_smem) ++spills;
@@ -720,6 +796,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     uint32_t* const P1 = in_smem ? sm.p1 : s.c_p1;
 
     // ---- phase 3: updated values of the live prefixes (blank / repeat / pulled extension), :150-256
+    float cand_min = 3.402823466e+38f, cand_max = kNegMax;   // over this thread's finite candidate scores (phase 5 bins)
     for (uint32_t j = tid; j < n_live; j += NT) {
       const float sj = L.score[j];
       const uint32_t cj = (L.chr[j] == (uint8_t)kRootChar) ? kRootChar : (uint32_t)L.chr[j];
@@ -774,6 +851,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         bcur = lp_b;  // log_sum_exp(-FLT_MAX, lp_b)
       }
       const float ns = sttmath::log_sum_exp(bcur, nb);
+      if (ns > kNegMax) { cand_min = fminf(cand_min, ns); cand_max = fmaxf(cand_max, ns); }
       K[j] = make_key(ns, cj, j);
       P0[j] = __float_as_uint(bcur);
       P1[j] = __float_as_uint(nb);
@@ -805,6 +883,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           lp += lm_t;
           lp = (float)((double)lp + sv.beta);
         }
+        if (lp > kNegMax) { cand_min = fminf(cand_min, lp); cand_max = fmaxf(cand_max, lp); }
         K[e] = make_key(lp, (uint32_t)c, e);
         P0[e] = ii | ((uint32_t)c << 16);   // the child's dictionary state is looked up in phase 6, for survivors only
       };
@@ -830,15 +909,105 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         }
       }
     }
-    __syncthreads();
+    {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        cand_min = fminf(cand_min, __shfl_xor_sync(0xffffffffu, cand_min, d));
+        cand_max = fmaxf(cand_max, __shfl_xor_sync(0xffffffffu, cand_max, d));
+      }
+      if ((tid & 31) == 0) { s_red[tid >> 5] = cand_min; s_red2[tid >> 5] = cand_max; }
+    }
+    main_sync<NT>();
     for (uint32_t i = tid; i < (uint32_t)WC; i += NT) sm.child[i] = 0;  // ready for the next step's phase 0
     if (have_next && tid < C) next_row_ready(cb ^ 1);
     PHASE_MARK(4);
 
-    // ---- phase 5: exact top-W radix select on the 64-bit key (:263-274 nth_element + prefix_compare)
-    //      two barriers per pass: warp 0 re-zeroes the histogram right after scanning it
+    // ---- phase 5: exact top-W selection on the 64-bit key (:263-274 nth_element + prefix_compare).
+    //      One pass: a kSelBins-bin histogram over [min, max] of the finite candidate scores (the bin is a monotone
+    //      function of the score, so everything in a higher bin beats everything in a lower one), a suffix scan finds
+    //      the bin the W-th best key falls in, and that bin's few members are ranked pairwise on the full key.  Five
+    //      barriers and no contended atomics, instead of two barriers per 8-bit radix pass with most keys landing in
+    //      one or two bins of the leading passes.  The radix passes remain as the fallback for a crowded boundary bin
+    //      (hundreds of equal scores, e.g. -FLT_MAX zombies at the boundary).
     unsigned long long sel_prefix = 0, sel_mask = 0;
-    if (N > (uint32_t)W) {
+    int sel_mode = 0;              // 0 keep all / radix predicate, 1 bin >= sel_bin, 2 key >= sel_key
+    uint32_t sel_bin = 0;
+    unsigned long long sel_key = 0;
+    float sel_lo = 0.f, sel_scale = 0.f;
+    auto bin_of = [&](unsigned long long key) -> uint32_t {
+      const float sc = unsortable((uint32_t)(key >> 32));
+      if (!(sc > kNegMax)) return 0u;
+      const float x = (sc - sel_lo) * sel_scale;
+      int b = (int)x;
+      b = b < 0 ? 0 : (b > kSelBins - 1 ? kSelBins - 1 : b);
+      return (uint32_t)b;
+    };
+    bool need_radix = (N > (uint32_t)W);
+    if (need_radix && (p.flags & kFlagHistSelect)) {
+      float lo = s_red[0], hi = s_red2[0];
+#pragma unroll
+      for (int w = 1; w < NT / 32; ++w) { lo = fminf(lo, s_red[w]); hi = fmaxf(hi, s_red2[w]); }
+      sel_lo = lo;
+      sel_scale = (hi > lo) ? (float)(kSelBins - 1) / (hi - lo) : 0.f;
+      for (uint32_t e = tid; e < N; e += NT) atomicAdd(&sel_hist[bin_of(K[e])], 1u);
+      main_sync<NT>();
+      // thread t owns bins [4t, 4t+4); higher bins = better scores, so count from the top
+      const uint4 hv = reinterpret_cast<const uint4*>(sel_hist)[tid];
+      const uint32_t mine = hv.x + hv.y + hv.z + hv.w;
+      uint32_t suffix = mine;   // inclusive over lanes >= this one
+      const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_down_sync(0xffffffffu, suffix, d);
+        if (lane + d < 32) suffix += o;
+      }
+      if (lane == 0) s_warp[warp] = suffix;
+      main_sync<NT>();
+      uint32_t above_warps = 0;
+#pragma unroll
+      for (int w = 1; w < NT / 32; ++w) above_warps += (w > warp) ? s_warp[w] : 0u;
+      const uint32_t incl = above_warps + suffix, above = incl - mine;
+      if (above < (uint32_t)W && incl >= (uint32_t)W) {
+        const uint32_t hq[4] = {hv.x, hv.y, hv.z, hv.w};
+        uint32_t cum = above;
+#pragma unroll
+        for (int q = 3; q >= 0; --q) {
+          if (cum + hq[q] >= (uint32_t)W) {
+            s_u[2] = (uint32_t)(tid * 4 + q);
+            s_u[3] = (uint32_t)W - cum;   // still needed from this bin
+            s_u[4] = hq[q];               // elements in this bin
+            s_u[1] = 0;                   // boundary list length
+            break;
+          }
+          cum += hq[q];
+        }
+      }
+      main_sync<NT>();
+      sel_bin = s_u[2];
+      const uint32_t k_rem = s_u[3], cnt = s_u[4];
+      if (cnt == k_rem) {
+        sel_mode = 1;            // the whole boundary bin is selected
+        need_radix = false;
+      } else if (cnt <= (uint32_t)kSelBoundaryCap) {
+        for (uint32_t e = tid; e < N; e += NT) {
+          const unsigned long long key = K[e];
+          if (bin_of(key) == sel_bin) sel_blist[atomicAdd(&s_u[1], 1u)] = key;
+        }
+        main_sync<NT>();
+        if ((uint32_t)tid < cnt) {
+          const unsigned long long mk = sel_blist[tid];
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < cnt; ++j) rank += (sel_blist[j] > mk) ? 1u : 0u;
+          if (rank == k_rem - 1) s_thresh = mk;   // keys are unique: exactly one thread
+        }
+        main_sync<NT>();
+        sel_key = s_thresh;
+        sel_mode = 2;
+        need_radix = false;
+      }
+      // else: crowded boundary bin -> radix passes below (every thread takes the same branch: cnt is shared)
+    }
+    if (need_radix) {
       uint32_t k_rem = (uint32_t)W;
       for (int pass = 7; pass >= 0; --pass) {
         const int shift = pass * 8;
@@ -846,7 +1015,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           const unsigned long long key = K[e];
           if ((key & sel_mask) == sel_prefix) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
         }
-        __syncthreads();
+        main_sync<NT>();
         if (tid < 32) {
           // lane l owns bins [8l, 8l+8); find the bin where the count from the top crosses k_rem
           uint32_t hc[8];
@@ -883,7 +1052,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
             }
           }
         }
-        __syncthreads();
+        main_sync<NT>();
         sel_prefix |= (unsigned long long)s_u[2] << shift;
         sel_mask |= (unsigned long long)255u << shift;
         k_rem = s_u[3];
@@ -909,12 +1078,14 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         bool keep = false;
         if (e < N) {
           key = K[e];
-          keep = (N <= (uint32_t)W) || ((key & sel_mask) >= sel_prefix);
+          keep = (N <= (uint32_t)W) || (sel_mode == 2 ? key >= sel_key
+                                        : sel_mode == 1 ? bin_of(key) >= sel_bin
+                                                        : (key & sel_mask) >= sel_prefix);
         }
         bal[q] = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) s_cnt[q * (NT / 32) + warp] = __popc(bal[q]);
       }
-      __syncthreads();
+      main_sync<NT>();
       if (warp == 0) {
         constexpr int PER = kCommitRounds * (NT / 32) / 32;  // entries per lane
         uint32_t v[PER], sum = 0;
@@ -931,7 +1102,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         for (int i = 0; i < PER; ++i) { s_cnt[lane * PER + i] = run; run += v[i]; }
         if (lane == 31) s_cnt[kCommitRounds * (NT / 32)] = incl;
       }
-      __syncthreads();
+      main_sync<NT>();
 #pragma unroll
       for (int q = 0; q < kCommitRounds; ++q) {
         const uint32_t e = g0 + (uint32_t)q * NT + tid;
@@ -980,7 +1151,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         }
       }
       out_base += s_cnt[kCommitRounds * (NT / 32)];
-      __syncthreads();
+      main_sync<NT>();
     }
     PHASE_MARK(7);
     // (ii) one thread per survivor.  A NEW survivor does the global-memory work (dictionary arc / arena node / child-list
@@ -1034,11 +1205,11 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
               if (pc == (uint32_t)(uint8_t)kRootChar || (int)pc == p.space_id) {
                 meta_init = 0u | (0u << 8) | (1u << 16);  // empty previous word: null context, an OOV inside the window
               } else {
-                meta_init = s.lm_meta[pnode];
+                meta_init = __ldcg(&s.lm_meta[pnode]);   // written by whoever evaluated the parent (maybe a helper warp)
                 const uint32_t len = meta_init == kNone ? 0u : (meta_init & 0xffu);
                 for (uint32_t q = 0; q < len && q < (uint32_t)kStateWords; ++q) {
-                  s.lm_sw[(size_t)id * kStateWords + q] = s.lm_sw[(size_t)pnode * kStateWords + q];
-                  s.lm_sb[(size_t)id * kStateWords + q] = s.lm_sb[(size_t)pnode * kStateWords + q];
+                  s.lm_sw[(size_t)id * kStateWords + q] = __ldcg(&s.lm_sw[(size_t)pnode * kStateWords + q]);
+                  s.lm_sb[(size_t)id * kStateWords + q] = __ldcg(&s.lm_sb[(size_t)pnode * kStateWords + q]);
                 }
               }
             } else if (p.fst_space_skip) {
@@ -1048,6 +1219,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
           }
           s.nodes[id] = n;
           s.lm_meta[id] = meta_init;
+          reinterpret_cast<unsigned long long*>(s.lm_cond)[id] = kLmUnset;
           ht_insert(s, pnode, c, id);
           atomicOr(&s.nodes[pnode].child_mask, 1u << c);
           if (np != kNone) atomicOr(&cmN[np], 1u << c);
@@ -1070,7 +1242,7 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
         Nx.ts[pos] = kNone;
       }
     }
-    __syncthreads();
+    main_sync<NT>();
     {
       // prefixes whose parent was not live may have just got it back: revived nodes announce their new slot
       const uint32_t n_rev = s_rs[cpar];
@@ -1097,6 +1269,10 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     }
     const uint32_t n_surv = out_base;
     arena_count = s_u[5];
+    if (tid == 0) {   // this commit's nodes (written before the barrier above) may now be read by the LM helper warps
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(&s_help[0]) = arena_count < s.arena_cap ? arena_count : s.arena_cap;
+    }
     ts_count += n_surv;
     if (arena_count > s.arena_cap || ts_count > s.ts_cap) overflow = 1;
     n_live = n_surv;
@@ -1106,7 +1282,8 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
 #undef PHASE_MARK
 
   // ---- store the live list for the next launch / finalize
-  __syncthreads();
+  if (tid == 0) *reinterpret_cast<volatile uint32_t*>(&s_help[1]) = 1u;   // helper warps: drain and leave
+  main_sync<NT>();
   {
     const LiveList<WC>& L = sm.live[cur];
     for (uint32_t i = tid; i < n_live; i += NT) {
@@ -1125,11 +1302,14 @@ __global__ void __launch_bounds__(NT) decoder_step_kernel(Slot* slots, const Ste
     s.scalars[4] = abs_t;
     s.scalars[5] = start_expanding;
     s.scalars[6] = overflow;
-    s.scalars[7] += s_u[6];   // words scored by the LM (reference-equivalent window sizes)
-    s.scalars[8] += s_u[7];   // LM calls
+    if (kInstr) {
+      s.scalars[7] += s_u[6];   // words scored by the LM (reference-equivalent window sizes)
+      s.scalars[8] += s_u[7];   // LM calls
+    }
     if (max_cand > s.scalars[9]) s.scalars[9] = max_cand;
     s.scalars[10] += spills;
-    for (int q = 0; q < 8; ++q) s.phase_cycles[q] += s_ph[q];
+    if (kInstr)
+      for (int q = 0; q < 8; ++q) s.phase_cycles[q] += s_ph[q];
   }
 }
 

@@ -7,9 +7,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <thread>
 
 #include "decoder.cuh"
@@ -102,17 +107,31 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
   return make_tmap(out, base, 2, dims, strides, box);
 }
 
+// Kernel attributes (opt-in shared memory) are per DEVICE: each Engine remembers which of its kernels it has configured
+// on its device in a bit mask.  Setting an attribute twice is harmless, so concurrent host threads need no lock.
+enum KernelBit {
+  kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
+  kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitDec512, kBitDec512N, kBitDec512I, kBitDec2048, kBitDec2048N, kBitDec2048I
+};
+template <class K>
+int ensure_smem(std::atomic<uint32_t>* mask, int bit, K kern, int bytes) {
+  if (mask->load(std::memory_order_acquire) & (1u << bit)) return 0;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  mask->fetch_or(1u << bit, std::memory_order_release);
+  return 0;
+}
+
 template <int BN, int EPI, int AMODE>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::GemmParams& p, int num_sms,
-                cudaStream_t st) {
+                cudaStream_t st, std::atomic<uint32_t>* cfg_mask) {
   constexpr int STAGES = (BN == 256) ? 4 : 6;
   using L = sttgemm::SmemLayout<BN, STAGES>;
   auto kern = sttgemm::gemm_tc_kernel<BN, STAGES, EPI, AMODE>;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  constexpr int bit = (AMODE == sttgemm::kWindows3D) ? kBitGemmWin
+                      : (EPI == sttgemm::kEpiClipReluF16) ? kBitGemmRelu
+                      : (EPI == sttgemm::kEpiBiasF32)     ? kBitGemmBias
+                                                          : kBitGemmSoftmax;
+  if (ensure_smem(cfg_mask, bit, kern, L::kTotal)) return -1;
   int n_tiles_m;
   if (AMODE == sttgemm::kWindows3D)
     n_tiles_m = ((p.T + p.t_box - 1) / p.t_box) * ((p.B + p.b_box - 1) / p.b_box);
@@ -147,6 +166,18 @@ struct Engine {
   int4* fst_arc4 = nullptr;     // per arc {child dictionary state, its first arc, its label mask, word-ordinal skip}
   uint32_t* fst_space_skip = nullptr;  // word-ordinal tables (decoder.cuh DecodeParams), null when not applicable
   uint32_t* ord2wid = nullptr;
+  // ---- launch state of THIS engine's device (nothing process-wide: one process may drive several GPUs)
+  std::atomic<uint32_t> cfg_mask{0};   // KernelBit: kernels whose attributes are set on this device
+  std::mutex launch_mu;                // guards the caches below
+  std::map<std::pair<int, int>, int> lstm_cluster;   // (M tiles, grid) -> cluster size that is co-resident
+  int lstm_pair_usable = -1, lstm_pp_usable[3] = {-1, -1, -1};
+  bool use_overlap_view = true;
+  bool lstm_noncoop = false;           // see launch_lstm_pp_inst
+  // ---- options, read ONCE when the engine is created (development switches; none is needed in production)
+  int opt_lstm_cluster_cap = 8, opt_lstm_pair = 1, opt_lstm_pp_mode = 4, opt_word_ordinals = 1;
+  int opt_dec_flags = sttdec::kFlagHistSelect | sttdec::kFlagLmHelper;
+  int opt_lstm_exact_h = 1;
+  bool verbose = false;
 };
 
 const sttmodel::HostModel& engine_model(const Engine* e) { return e->hm; }
@@ -301,6 +332,20 @@ Engine* engine_create(const sttmodel::HostModel& m, std::string* err) {
   Engine* e = new Engine();
   e->hm = m;
   cudaGetDevice(&e->device);
+  {
+    auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+    e->opt_lstm_cluster_cap = std::max(1, geti("STT_B200_LSTM_CLUSTER", 8));
+    e->opt_lstm_pair = geti("STT_B200_LSTM_PAIR", 1);
+    e->opt_lstm_pp_mode = geti("STT_B200_LSTM_PINGPONG", 4);
+    e->opt_word_ordinals = getenv("STT_B200_NO_WORD_ORDINALS") ? 0 : 1;
+    e->opt_dec_flags = geti("STT_B200_DEC_FLAGS", e->opt_dec_flags);
+    e->opt_lstm_exact_h = geti("STT_B200_LSTM_EXACT_H", 1);
+    e->verbose = getenv("STT_B200_VERBOSE") != nullptr;
+    // A CUDA injection library (Nsight Compute / Systems) serialises kernels and, with this driver, fails launches that
+    // carry BOTH the cooperative and the cluster attribute; see launch_lstm_*.
+    e->lstm_noncoop = getenv("STT_B200_LSTM_NONCOOP") != nullptr || getenv("CUDA_INJECTION64_PATH") != nullptr ||
+                      getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") != nullptr;
+  }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, e->device);
   e->num_sms = prop.multiProcessorCount;
@@ -579,10 +624,12 @@ struct Batch {
   int last_run_T = 0;
   StageTimes times;
   long long launches = 0;
+  bool instrument = false;   // decoder statistics build (per-phase clocks, LM counters); bench.py asks for it once
 };
 
 const StageTimes& batch_times(const Batch* b) { return b->times; }
 long long batch_kernel_launches(const Batch* b) { return b->launches; }
+void batch_set_instrumented(Batch* b, bool on) { b->instrument = on; }
 int batch_T(const Batch* b, int utt) { return (utt >= 0 && utt < b->B) ? b->T[utt] : -1; }
 
 namespace {
@@ -794,65 +841,122 @@ int batch_upload(Batch* b, const int16_t* const* pcm, const unsigned* n_samples,
 namespace {
 
 
+// Every LSTM kernel is ONE launch for all T steps with a device-wide barrier per step, so all of its CTAs must be
+// co-resident: the launch is cooperative (the runtime refuses it otherwise) and the occupancy query below is checked
+// first.  Exception: with a profiler attached (Engine::lstm_noncoop) the cooperative attribute is dropped, because this
+// driver fails cooperative + cluster launches under Nsight Compute ("LaunchFailed"); a profiler serialises kernels, so
+// the co-residency that the occupancy query established still holds.  The same fallback is taken once if a cooperative
+// launch is refused synchronously.
+template <class K, class... Args>
+int launch_coop_cluster(Engine* e, K kern, cudaLaunchConfig_t cfgl, int cluster, Args... args) {
+  cudaLaunchAttribute attrs[2];
+  int n = 0;
+  if (!e->lstm_noncoop) {
+    attrs[n].id = cudaLaunchAttributeCooperative;
+    attrs[n].val.cooperative = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attrs[n].id = cudaLaunchAttributeClusterDimension;
+    attrs[n].val.clusterDim.x = cluster;
+    attrs[n].val.clusterDim.y = 1;
+    attrs[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfgl.attrs = attrs;
+  cfgl.numAttrs = n;
+  cudaError_t err = cudaLaunchKernelEx(&cfgl, kern, args...);
+  if (err != cudaSuccess && !e->lstm_noncoop && cluster > 1) {
+    cudaGetLastError();
+    fprintf(stderr, "[stt_b200] cooperative + cluster launch refused (%s); co-residency was verified by the occupancy query, "
+                    "retrying without the cooperative attribute\n", cudaGetErrorString(err));
+    e->lstm_noncoop = true;
+    attrs[0] = attrs[1];
+    cfgl.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfgl, kern, args...);
+  }
+  if (err != cudaSuccess) {
+    fprintf(stderr, "[stt_b200] LSTM launch failed: %s\n", cudaGetErrorString(err));
+    return -1;
+  }
+  return 0;
+}
+
+// how many CTAs of `kern` (cluster size `cluster`) can be resident at once
+template <class K>
+long long resident_ctas(Engine* e, K kern, int threads, int smem, int grid, int cluster) {
+  if (cluster > 1) {
+    cudaLaunchConfig_t c{};
+    c.gridDim = dim3(grid);
+    c.blockDim = dim3(threads);
+    c.dynamicSmemBytes = smem;
+    cudaLaunchAttribute a[1];
+    a[0].id = cudaLaunchAttributeClusterDimension;
+    a[0].val.clusterDim.x = cluster;
+    a[0].val.clusterDim.y = 1;
+    a[0].val.clusterDim.z = 1;
+    c.attrs = a;
+    c.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &c) != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
+    return (long long)n_clusters * cluster;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+  return (long long)per_sm * e->num_sms;
+}
+
 template <int MT, int STAGES, int CS>
 int launch_lstm_inst(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st, bool probe_only, bool* fits) {
   using L = sttlstm::SmemLayout<MT, STAGES>;
+  Engine* e = b->e;
   auto kern = sttlstm::lstm_tc_kernel<MT, STAGES, CS>;
-  static bool cfg = false;
-  if (!cfg) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    cfg = true;
+  constexpr int cs_idx = CS == 8 ? 3 : CS == 4 ? 2 : CS == 2 ? 1 : 0;
+  if (ensure_smem(&e->cfg_mask, (MT == 1 ? kBitLstm1 : kBitLstm2) + cs_idx, kern, L::kTotal)) return -1;
+  if (probe_only) {
+    *fits = resident_ctas(e, kern, sttlstm::kNumThreads, L::kTotal, grid, CS) >= grid;
+    return 0;
   }
   cudaLaunchConfig_t cfgl{};
   cfgl.gridDim = dim3(grid);
   cfgl.blockDim = dim3(sttlstm::kNumThreads);
   cfgl.dynamicSmemBytes = L::kTotal;
   cfgl.stream = st;
-  cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeCooperative;
-  attrs[0].val.cooperative = 1;
-  attrs[1].id = cudaLaunchAttributeClusterDimension;
-  attrs[1].val.clusterDim.x = CS;
-  attrs[1].val.clusterDim.y = 1;
-  attrs[1].val.clusterDim.z = 1;
-  cfgl.attrs = attrs;
-  cfgl.numAttrs = (CS > 1) ? 2 : 1;
-  if (probe_only) {
-    // all CTAs must be co-resident (device-wide barrier): how many clusters of this size fit at once?
-    int n_clusters = 0;
-    if (CS > 1) {
-      if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfgl) != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
-    } else {
-      int per_sm = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sttlstm::kNumThreads, L::kTotal);
-      n_clusters = per_sm * b->e->num_sms;
-    }
-    *fits = (long long)n_clusters * CS >= grid;
-    return 0;
-  }
   // A-operand tensor map with a 128/CS-row box (each CTA of a cluster fetches one slice and multicasts it)
   CUtensorMap tm_h;
   const size_t rows = (size_t)b->T_cap * b->B_cap + b->B_cap + 256;
-  if (!make_tmap_2d(&tm_h, b->d_hall, rows, b->e->Cp, b->e->Cp, 128 / CS)) return -1;
-  CUDA_OK(cudaLaunchKernelEx(&cfgl, kern, tm_h, b->e->tm_wh, lp));
-  return 0;
+  if (!make_tmap_2d(&tm_h, b->d_hall, rows, e->Cp, e->Cp, 128 / CS)) return -1;
+  if (CS == 1 && e->lstm_noncoop) {   // no cluster attribute to keep: plain launch (profiler only)
+    kern<<<grid, sttlstm::kNumThreads, L::kTotal, st>>>(tm_h, e->tm_wh, lp);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  return launch_coop_cluster(e, kern, cfgl, CS, tm_h, e->tm_wh, lp);
 }
 
 template <int MT, int STAGES>
 int launch_lstm_mt(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st) {
   // largest cluster size that divides the grid AND lets the whole grid be co-resident (GPC sizes vary per part)
-  static int chosen[1024] = {0};  // by grid size
-  int cs = (grid < 1024) ? chosen[grid] : 0;
-  if (cs == 0) {
-    static const char* force = getenv("STT_B200_LSTM_CLUSTER");  // debugging aid: 1 disables multicast
-    const int cap = force ? std::max(1, atoi(force)) : 8;
-    bool fits = false;
-    cs = 1;
-    if (cap >= 8 && grid % 8 == 0 && launch_lstm_inst<MT, STAGES, 8>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 8;
-    else if (cap >= 4 && grid % 4 == 0 && launch_lstm_inst<MT, STAGES, 4>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 4;
-    else if (cap >= 2 && grid % 2 == 0 && launch_lstm_inst<MT, STAGES, 2>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 2;
-    if (grid < 1024) chosen[grid] = cs;
-    if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] LSTM grid %d: cluster size %d\n", grid, cs);
+  Engine* e = b->e;
+  int cs = 0;
+  {
+    std::lock_guard<std::mutex> lk(e->launch_mu);
+    auto it = e->lstm_cluster.find({MT, grid});
+    if (it != e->lstm_cluster.end()) cs = it->second;
+    if (cs == 0) {
+      const int cap = e->opt_lstm_cluster_cap;
+      bool fits = false;
+      cs = 1;
+      if (cap >= 8 && grid % 8 == 0 && launch_lstm_inst<MT, STAGES, 8>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 8;
+      else if (cap >= 4 && grid % 4 == 0 && launch_lstm_inst<MT, STAGES, 4>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 4;
+      else if (cap >= 2 && grid % 2 == 0 && launch_lstm_inst<MT, STAGES, 2>(b, lp, grid, st, true, &fits) == 0 && fits) cs = 2;
+      else if (launch_lstm_inst<MT, STAGES, 1>(b, lp, grid, st, true, &fits) != 0 || !fits) {
+        fprintf(stderr, "[stt_b200] the LSTM grid (%d CTAs) cannot be co-resident on this device\n", grid);
+        return -1;
+      }
+      e->lstm_cluster[{MT, grid}] = cs;
+      if (e->verbose) fprintf(stderr, "[stt_b200] LSTM grid %d: cluster size %d\n", grid, cs);
+    }
   }
   bool unused;
   if (cs == 8) return launch_lstm_inst<MT, STAGES, 8>(b, lp, grid, st, false, &unused);
@@ -863,76 +967,55 @@ int launch_lstm_mt(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream
 
 // CTA-pair (cta_group::2) kernel for 129..256 utterances; returns 1 if it cannot be used.
 int launch_lstm_pair(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st) {
-  static int usable = -1;  // -1 unknown, 0 no, 1 yes
-  static const char* env = getenv("STT_B200_LSTM_PAIR");
-  if (env && atoi(env) == 0) return 1;
-  if (grid % 2 != 0) return 1;
+  Engine* e = b->e;
+  if (e->opt_lstm_pair == 0 || grid % 2 != 0) return 1;
   using L = sttlstm::PairSmem;
   auto kern = sttlstm::lstm_pair_kernel;
+  {
+    std::lock_guard<std::mutex> lk(e->launch_mu);
+    if (e->lstm_pair_usable < 0) {
+      e->lstm_pair_usable = 0;
+      if (ensure_smem(&e->cfg_mask, kBitLstmPair, kern, L::kTotal) == 0)
+        e->lstm_pair_usable = resident_ctas(e, kern, sttlstm::kNumThreads, L::kTotal, grid, 2) >= grid ? 1 : 0;
+      if (e->verbose) fprintf(stderr, "[stt_b200] LSTM pair kernel usable=%d\n", e->lstm_pair_usable);
+    }
+    if (!e->lstm_pair_usable) return 1;
+  }
   cudaLaunchConfig_t cfgl{};
   cfgl.gridDim = dim3(grid);
   cfgl.blockDim = dim3(sttlstm::kNumThreads);
   cfgl.dynamicSmemBytes = L::kTotal;
   cfgl.stream = st;
-  cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeCooperative;
-  attrs[0].val.cooperative = 1;
-  attrs[1].id = cudaLaunchAttributeClusterDimension;
-  attrs[1].val.clusterDim.x = 2;
-  attrs[1].val.clusterDim.y = 1;
-  attrs[1].val.clusterDim.z = 1;
-  cfgl.attrs = attrs;
-  cfgl.numAttrs = 2;
-  if (usable < 0) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) { cudaGetLastError(); usable = 0; return 1; }
-    int n_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfgl) != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
-    usable = (n_clusters * 2 >= grid) ? 1 : 0;
-    if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] LSTM pair kernel: %d co-resident pairs, usable=%d\n", n_clusters, usable);
-  }
-  if (!usable) return 1;
   CUtensorMap tm_h;
   const size_t rows = (size_t)b->T_cap * b->B_cap + b->B_cap + 256;
-  if (!make_tmap_2d(&tm_h, b->d_hall, rows, b->e->Cp, b->e->Cp, 128)) return -1;
-  CUDA_OK(cudaLaunchKernelEx(&cfgl, kern, tm_h, b->e->tm_wh, lp));
-  return 0;
+  if (!make_tmap_2d(&tm_h, b->d_hall, rows, e->Cp, e->Cp, 128)) return -1;
+  return launch_coop_cluster(e, kern, cfgl, 2, tm_h, e->tm_wh, lp);
 }
 
 // Ping-pong CTA-pair kernel (two groups of <= 128 utterances, M = 128 MMAs); returns 1 if it cannot be used.
 template <int KB, int STAGES>
 int launch_lstm_pp_inst(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st) {
-  static int usable = -1;  // -1 unknown, 0 no, 1 yes
+  Engine* e = b->e;
   using L = sttlstm::PPSmem<KB, STAGES>;
   auto kern = sttlstm::lstm_pp_kernel<KB, STAGES>;
+  constexpr int idx = KB == 4 ? 0 : KB == 2 ? 1 : 2;
+  {
+    std::lock_guard<std::mutex> lk(e->launch_mu);
+    if (e->lstm_pp_usable[idx] < 0) {
+      e->lstm_pp_usable[idx] = 0;
+      if (ensure_smem(&e->cfg_mask, kBitLstmPP4 + idx, kern, L::kTotal) == 0)
+        e->lstm_pp_usable[idx] = resident_ctas(e, kern, sttlstm::kPPThreads, L::kTotal, grid, 2) >= grid ? 1 : 0;
+      if (e->verbose) fprintf(stderr, "[stt_b200] LSTM ping-pong kernel<%d,%d> usable=%d\n", KB, STAGES, e->lstm_pp_usable[idx]);
+    }
+    if (!e->lstm_pp_usable[idx]) return 1;
+  }
   cudaLaunchConfig_t cfgl{};
   cfgl.gridDim = dim3(grid);
   cfgl.blockDim = dim3(sttlstm::kPPThreads);
   cfgl.dynamicSmemBytes = L::kTotal;
   cfgl.stream = st;
-  cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeCooperative;
-  attrs[0].val.cooperative = 1;
-  attrs[1].id = cudaLaunchAttributeClusterDimension;
-  attrs[1].val.clusterDim.x = 2;
-  attrs[1].val.clusterDim.y = 1;
-  attrs[1].val.clusterDim.z = 1;
-  cfgl.attrs = attrs;
-  cfgl.numAttrs = 2;
-  // Nsight Compute (2025.2, driver 580) fails cooperative + cluster launches with "LaunchFailed".  For PROFILING runs
-  // only, STT_B200_LSTM_NONCOOP=1 drops the cooperative attribute: ncu serialises kernels, so the 128 one-per-SM CTAs
-  // are co-resident anyway; production launches keep the guarantee.
-  static const bool noncoop = getenv("STT_B200_LSTM_NONCOOP") != nullptr;
-  if (noncoop) { attrs[0] = attrs[1]; cfgl.numAttrs = 1; }
-  if (usable < 0) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) { cudaGetLastError(); usable = 0; return 1; }
-    int n_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfgl) != cudaSuccess) { cudaGetLastError(); n_clusters = 0; }
-    usable = (n_clusters * 2 >= grid) ? 1 : 0;
-    if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] LSTM ping-pong kernel<%d,%d>: %d co-resident pairs, usable=%d\n", KB, STAGES, n_clusters, usable);
-  }
-  if (!usable) return 1;
   // 3-D views {64 columns, rows, K block}: one request brings KB K blocks of 64 rows
-  const int Cp = b->e->Cp;
+  const int Cp = e->Cp;
   CUtensorMap tm_h, tm_w;
   {
     const uint64_t rows = (uint64_t)b->T_cap * b->B_cap + b->B_cap + 256;
@@ -941,14 +1024,12 @@ int launch_lstm_pp_inst(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaS
     uint32_t box[3] = {64, 64, (uint32_t)KB};
     if (!make_tmap(&tm_h, b->d_hall, 3, dims, strides, box)) return 1;
     dims[1] = (uint64_t)4 * Cp;
-    if (!make_tmap(&tm_w, b->e->wh, 3, dims, strides, box)) return 1;
+    if (!make_tmap(&tm_w, e->wh, 3, dims, strides, box)) return 1;
   }
-  CUDA_OK(cudaLaunchKernelEx(&cfgl, kern, tm_h, tm_w, lp));
-  return 0;
+  return launch_coop_cluster(e, kern, cfgl, 2, tm_h, tm_w, lp);
 }
 int launch_lstm_pp(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream_t st) {
-  static const char* env = getenv("STT_B200_LSTM_PINGPONG");
-  const int mode = env ? atoi(env) : 4;
+  const int mode = b->e->opt_lstm_pp_mode;
   if (mode == 0 || grid % 2 != 0) return 1;
   if (mode == 2) return launch_lstm_pp_inst<2, 6>(b, lp, grid, st);
   if (mode == 1) return launch_lstm_pp_inst<1, 12>(b, lp, grid, st);
@@ -977,14 +1058,14 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
   while (b_box < B && b_box < 128) b_box <<= 1;
   const int t_box = 128 / b_box;
   CUtensorMap tm_feat;
-  static bool use_overlap_view = true;
+  bool use_overlap_view = e->use_overlap_view;
   if (use_overlap_view) {
     uint64_t dims[3] = {(uint64_t)e->K1, (uint64_t)(b->rows_per_utt - 2 * m.n_context), (uint64_t)b->B_cap};
     uint64_t strides[2] = {64, (uint64_t)b->rows_per_utt * 64};
     uint32_t box[3] = {64, (uint32_t)t_box, (uint32_t)b_box};
     if (!make_tmap(&tm_feat, b->d_feat, 3, dims, strides, box)) {
       fprintf(stderr, "[stt_b200] overlapping-row tensor map rejected; using the gathered window matrix\n");
-      use_overlap_view = false;
+      use_overlap_view = e->use_overlap_view = false;
     }
   }
   sttgemm::GemmParams p{};
@@ -993,7 +1074,7 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
   if (time_it) cudaEventRecord(b->ev[3], st);
   p.M = M; p.N = Hp; p.K = round_up(e->K1, 64); p.bias = e->b1; p.out = b->d_act_a;
   if (use_overlap_view) {
-    if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kWindows3D>(tm_feat, e->tm_w1, p, e->num_sms, st)) return -1;
+    if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kWindows3D>(tm_feat, e->tm_w1, p, e->num_sms, st, &e->cfg_mask)) return -1;
   } else {
     const int K1p = round_up(e->K1, 64);
     if (!b->d_winmat) {
@@ -1004,16 +1085,16 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
     }
     gather_windows_kernel<<<M, 128, 0, st>>>(b->d_feat, b->d_winmat, B, T, b->rows_per_utt, e->K1, K1p);
     CUDA_OK(cudaGetLastError());
-    if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_winmat, e->tm_w1, p, e->num_sms, st)) return -1;
+    if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_winmat, e->tm_w1, p, e->num_sms, st, &e->cfg_mask)) return -1;
   }
   p.K = Hp; p.bias = e->b2; p.out = b->d_act_b;
-  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_a, e->tm_w2, p, e->num_sms, st)) return -1;
+  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_a, e->tm_w2, p, e->num_sms, st, &e->cfg_mask)) return -1;
   p.bias = e->b3; p.out = b->d_act_a;
-  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_b, e->tm_w3, p, e->num_sms, st)) return -1;
+  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_b, e->tm_w3, p, e->num_sms, st, &e->cfg_mask)) return -1;
   if (time_it) cudaEventRecord(b->ev[4], st);
   // ---- hoisted input half of the LSTM matmul (+ bias)
   p.N = 4 * Cp; p.K = Hp; p.bias = e->bx; p.out = b->d_xw;
-  if (launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(b->tm_act_a, e->tm_wx, p, e->num_sms, st)) return -1;
+  if (launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(b->tm_act_a, e->tm_wx, p, e->num_sms, st, &e->cfg_mask)) return -1;
   if (time_it) cudaEventRecord(b->ev[5], st);
   // ---- recurrence
   {
@@ -1022,6 +1103,7 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
     lp.B = B; lp.T = T; lp.n_cell = Cp; lp.xw = b->d_xw; lp.h_all = b->d_hall; lp.c_state = b->d_c; lp.h_state = b->d_h;
     lp.barrier = b->d_barrier;
     lp.prof = b->d_lstm_prof;
+    lp.exact_h = e->opt_lstm_exact_h;
     const int grid = Cp / sttlstm::kCellsPerCta;
     if (launch_lstm(b, lp, grid, B, st)) return -1;
   }
@@ -1030,10 +1112,10 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
   CUtensorMap tm_h_out;
   if (!make_tmap_2d(&tm_h_out, b->d_hall + (size_t)B * Cp, (uint64_t)M + 128, Cp, Cp, 128)) return -1;
   p.N = Hp; p.K = Cp; p.bias = e->b5; p.out = b->d_act_b;
-  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(tm_h_out, e->tm_w5, p, e->num_sms, st)) return -1;
+  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(tm_h_out, e->tm_w5, p, e->num_sms, st, &e->cfg_mask)) return -1;
   p.N = 32; p.K = Hp; p.bias = e->b6; p.out = b->d_probs; p.n_valid = m.n_classes;
   p.out_T_stride = b->T_cap; p.out_t_offset = out_t_offset;
-  if (launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(b->tm_act_b, e->tm_w6, p, e->num_sms, st)) return -1;
+  if (launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(b->tm_act_b, e->tm_w6, p, e->num_sms, st, &e->cfg_mask)) return -1;
   if (time_it) cudaEventRecord(b->ev[7], st);
   b->launches += 7;
   return 0;
@@ -1091,7 +1173,8 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
   if (e->has_scorer) dp.scorer = e->scorer_view;
   dp.fst_state2 = e->fst_state2;
   dp.fst_arc4 = e->fst_arc4;
-  dp.fst_space_skip = getenv("STT_B200_NO_WORD_ORDINALS") ? nullptr : e->fst_space_skip;
+  dp.fst_space_skip = e->opt_word_ordinals ? e->fst_space_skip : nullptr;
+  dp.flags = e->opt_dec_flags;
   dp.ord2wid = dp.fst_space_skip ? e->ord2wid : nullptr;
   dp.n_hot = e->has_scorer ? (int)std::min<size_t>(b->hot_ids.size(), sttdec::kMaxHotWords) : 0;
   for (int h = 0; h < dp.n_hot; ++h) {
@@ -1120,23 +1203,31 @@ int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& i
   cudaStream_t st = b->st;
   CUDA_OK(cudaMemcpyAsync(b->d_inputs, in.data(), sizeof(sttdec::StepInput) * n_slots, cudaMemcpyHostToDevice, st));
   const sttdec::DecodeParams dp = make_decode_params(b, beam);
-  constexpr int NT = 512;
+  constexpr int NT = 512, HW = sttdec::kHelperWarps;
+  Engine* e = b->e;
+  // instantiation: beam capacity x {production with LM helper warps, production without, statistics build}
+  const int variant = b->instrument ? 2 : ((e->opt_dec_flags & sttdec::kFlagLmHelper) ? 0 : 1);
+  auto go = [&](auto kern, int bit, size_t smem, int threads) -> int {
+    if (ensure_smem(&e->cfg_mask, bit, kern, (int)smem)) return -1;
+    kern<<<n_slots, threads, smem, st>>>(b->d_slots, b->d_inputs, dp);
+    return 0;
+  };
+  int rc;
   if (b->beam_cap <= 512) {
-    using SM = sttdec::StepSmem<512, 3072>;
-    auto kern = sttdec::decoder_step_kernel<NT, 512, 3072>;
-    static bool cfg = false;
-    if (!cfg) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM))); cfg = true; }
-    kern<<<n_slots, NT, sizeof(SM), st>>>(b->d_slots, b->d_inputs, dp);
+    constexpr size_t SM = sizeof(sttdec::StepSmem<512, 3072>);
+    rc = variant == 0   ? go(sttdec::decoder_step_kernel<NT, 512, 3072, false, HW>, kBitDec512, SM, NT + 32 * HW)
+         : variant == 1 ? go(sttdec::decoder_step_kernel<NT, 512, 3072, false, 0>, kBitDec512N, SM, NT)
+                        : go(sttdec::decoder_step_kernel<NT, 512, 3072, true, 0>, kBitDec512I, SM, NT);
   } else if (b->beam_cap <= 2048) {
-    using SM = sttdec::StepSmem<2048, 0>;
-    auto kern = sttdec::decoder_step_kernel<NT, 2048, 0>;
-    static bool cfg = false;
-    if (!cfg) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM))); cfg = true; }
-    kern<<<n_slots, NT, sizeof(SM), st>>>(b->d_slots, b->d_inputs, dp);
+    constexpr size_t SM = sizeof(sttdec::StepSmem<2048, 0>);
+    rc = variant == 0   ? go(sttdec::decoder_step_kernel<NT, 2048, 0, false, HW>, kBitDec2048, SM, NT + 32 * HW)
+         : variant == 1 ? go(sttdec::decoder_step_kernel<NT, 2048, 0, false, 0>, kBitDec2048N, SM, NT)
+                        : go(sttdec::decoder_step_kernel<NT, 2048, 0, true, 0>, kBitDec2048I, SM, NT);
   } else {
     fprintf(stderr, "[stt_b200] beam widths above 2048 are not supported by the shared-memory decoder\n");
     return -1;
   }
+  if (rc) return -1;
   CUDA_OK(cudaGetLastError());
   b->launches += 1;
   return 0;
@@ -1527,11 +1618,12 @@ int debug_gemm(int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   int rc = 0;
+  std::atomic<uint32_t> mask{0};
   for (int it = 0; it < 2 && rc == 0; ++it) {  // second run is the timed one
     cudaEventRecord(e0, 0);
-    if (epi == sttgemm::kEpiClipReluF16) rc = launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(ta, tb, p, sms, 0);
-    else if (epi == sttgemm::kEpiBiasF32) rc = launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(ta, tb, p, sms, 0);
-    else rc = launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(ta, tb, p, sms, 0);
+    if (epi == sttgemm::kEpiClipReluF16) rc = launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
+    else if (epi == sttgemm::kEpiBiasF32) rc = launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
+    else rc = launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
     cudaEventRecord(e1, 0);
     if (cudaDeviceSynchronize() != cudaSuccess) rc = -1;
   }

@@ -47,6 +47,7 @@ int batch_decode(Batch* b, int beam, int num_results);       // resets the decod
 int batch_fetch(Batch* b, std::vector<std::vector<Decoded>>* out);
 const StageTimes& batch_times(const Batch* b);
 long long batch_kernel_launches(const Batch* b);
+void batch_set_instrumented(Batch* b, bool on);              // decoder statistics build (phase clocks, LM counters) for the next decodes
 // Debug / test access
 int batch_phase_cycles(Batch* b, unsigned long long* out8);  // instrumentation: summed over utterances
 int batch_lstm_profile(Batch* b, unsigned long long* out3);  // max over CTAs: barrier-wait, load+MMA span, epilogue cycles

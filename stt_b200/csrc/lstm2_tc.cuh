@@ -218,7 +218,7 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
           const float go = __uint_as_float(r[q * 4 + 3]) + xv[cell].w;
           const float cn = sigmoid_fast(gf) * c_reg[cell] + sigmoid_fast(gi) * tanh_fast(gj);
           c_reg[cell] = cn;
-          h_last[cell] = sigmoid_mufu(go) * tanh_mufu(cn);
+          h_last[cell] = (p.exact_h ? sigmoid_fast(go) * tanh_fast(cn) : sigmoid_mufu(go) * tanh_mufu(cn));
         }
       }
       if (valid) {
@@ -485,7 +485,7 @@ lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
             const float go = __uint_as_float(r[q * 4 + 3]) + xv[q].w;
             const float cn = sigmoid_fast(gf) * c_reg[g][q] + sigmoid_fast(gi) * tanh_fast(gj);
             c_reg[g][q] = cn;
-            h_last[q] = sigmoid_mufu(go) * tanh_mufu(cn);
+            h_last[q] = (p.exact_h ? sigmoid_fast(go) * tanh_fast(cn) : sigmoid_mufu(go) * tanh_mufu(cn));
           }
         }
         if (ok) {

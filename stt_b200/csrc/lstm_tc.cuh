@@ -45,6 +45,7 @@ struct LstmParams {
   float* h_state;        // [B, n_cell] fp32 out (final h, full precision)
   unsigned int* barrier; // zero-initialised counter
   unsigned long long* prof; // [gridDim.x * 4] instrumentation (cycles): grid-barrier wait, load+MMA span, epilogue, -
+  int exact_h;           // h = sigmoid(o) * tanh(c) through the ex2/rcp forms (~1e-7 abs) instead of tanh.approx (2^-11 rel)
 };
 
 template <int MT, int STAGES>
@@ -240,7 +241,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           const float go = __uint_as_float(r[q * 4 + 3]) + xv[mt][q].w;
           const float cn = sigmoid_fast(gf) * c_reg[mt][q] + sigmoid_fast(gi) * tanh_fast(gj);
           c_reg[mt][q] = cn;
-          h_last[q] = sigmoid_mufu(go) * tanh_mufu(cn);
+          h_last[q] = (p.exact_h ? sigmoid_fast(go) * tanh_fast(cn) : sigmoid_mufu(go) * tanh_mufu(cn));
         }
         if (valid) {
           uint32_t hpk[4];
