@@ -27,7 +27,7 @@ $(BUILD)/%.o: $(SRC)/%.cc $(HDRS)
 	@mkdir -p $(BUILD)
 	$(CXX) $(CXXFLAGS) -I$(CUDA_HOME)/include -c $< -o $@
 
-$(OUT): $(BUILD)/engine.o $(BUILD)/capi.o $(BUILD)/model_file.o $(BUILD)/scorer_image.o
+$(OUT): $(BUILD)/engine.o $(BUILD)/capi.o $(BUILD)/model_file.o $(BUILD)/tflite_reader.o $(BUILD)/scorer_image.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -Xlinker --exclude-libs,ALL
 
 oracle:

@@ -192,6 +192,13 @@ STT_EXPORT int STTX_BatchSetProbs64(STTX_Batch* b, const double* probs, const in
 STT_EXPORT int STTX_DebugPairLayout(int M, float* out);
 STT_EXPORT int STTX_DebugGemm(int M, int N, int K, const unsigned short* a_f16, const unsigned short* w_f16,
                               const float* bias, int epilogue, float relu_clip, void* out, float* ms);
+/* Model-file inspection without a device: parses a TFLite flatbuffer (the reference's container,
+ * native_client/tflitemodelstate.cc:161-338) or a .sttw file exactly as STT_CreateModel does.  aInfo[12] = sample_rate,
+ * win_len, win_step, n_input, n_context, n_hidden, n_cell, n_classes, n_steps, beam_width, space_label, n_labels. */
+STT_EXPORT int STTX_InspectModel(const char* aModelBuffer, unsigned int aBufferSize, unsigned int* aInfo, float* aReluClip);
+/* fp32 copy of one tensor ("w1".."b6", "lstm_kernel", "lstm_bias") in TF layout; returns its element count */
+STT_EXPORT long long STTX_InspectModelTensor(const char* aModelBuffer, unsigned int aBufferSize, const char* aName,
+                                             float* aOut, unsigned long long aCapacity);
 STT_EXPORT int STTX_ModelInfo(const ModelState* aCtx, unsigned int* n_classes, unsigned int* n_input, unsigned int* n_hidden,
                               unsigned int* n_steps, unsigned int* n_sms);
 

@@ -55,7 +55,7 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchSetInstrumented", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout", "STTX_InspectModel", "STTX_InspectModelTensor",
 ]
 
 
@@ -126,6 +126,9 @@ def lib():
     L.STTX_BatchGetTimings.argtypes = [vp, POINTER(_Timings)]
     L.STTX_BatchKernelLaunches.argtypes = [vp]
     L.STTX_BatchSetInstrumented.argtypes = [vp, c_int]
+    L.STTX_InspectModel.argtypes = [c_char_p, c_uint, POINTER(c_uint), POINTER(c_float)]
+    L.STTX_InspectModelTensor.argtypes = [c_char_p, c_uint, c_char_p, c_void_p, ctypes.c_ulonglong]
+    L.STTX_InspectModelTensor.restype = c_longlong
     L.STTX_BatchKernelLaunches.restype = c_longlong
     L.STTX_BatchTimesteps.argtypes = [vp, c_uint]
     L.STTX_BatchPhaseCycles.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
@@ -294,6 +297,27 @@ class Model(object):
         v = [c_uint() for _ in range(5)]
         lib().STTX_ModelInfo(self._impl, *[byref(x) for x in v])
         return dict(zip(("n_classes", "n_input", "n_hidden", "n_steps", "n_sms"), [x.value for x in v]))
+
+
+def inspect_model(data):
+    """Parse model-file bytes (.tflite flatbuffer or .sttw) without a device; returns (info dict, tensors dict)."""
+    buf = bytes(data)
+    info = (c_uint * 12)()
+    clip = c_float()
+    status = lib().STTX_InspectModel(buf, len(buf), info, byref(clip))
+    if status != 0:
+        raise STTError("model file rejected: {} (0x{:X})".format(_err(status), status))
+    names = ("sample_rate", "win_len", "win_step", "n_input", "n_context", "n_hidden", "n_cell", "n_classes", "n_steps",
+             "beam_width", "space_label", "n_labels")
+    out = dict(zip(names, [int(x) for x in info]))
+    out["relu_clip"] = clip.value
+    tensors = {}
+    for n in ("w1", "b1", "w2", "b2", "w3", "b3", "lstm_kernel", "lstm_bias", "w5", "b5", "w6", "b6"):
+        cnt = lib().STTX_InspectModelTensor(buf, len(buf), n.encode(), None, 0)
+        arr = np.zeros(cnt, np.float32)
+        lib().STTX_InspectModelTensor(buf, len(buf), n.encode(), arr.ctypes.data, cnt)
+        tensors[n] = arr
+    return out, tensors
 
 
 class Stream(object):

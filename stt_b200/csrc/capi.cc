@@ -606,6 +606,36 @@ int STTX_ModelInfo(const ModelState* aCtx, unsigned int* n_classes, unsigned int
   return STT_ERR_OK;
 }
 
+// Model-file inspection without a device: parses either container (TFLite flatbuffer / .sttw) exactly as STT_CreateModel
+// does and reports what was read.  aInfo[12] = sample_rate, win_len, win_step, n_input, n_context, n_hidden, n_cell,
+// n_classes, n_steps, beam_width, space_label, number of labels.
+int STTX_InspectModel(const char* aModelBuffer, unsigned int aBufferSize, unsigned int* aInfo, float* aReluClip) {
+  sttmodel::HostModel hm;
+  const int err = sttmodel::load_from_buffer(reinterpret_cast<const uint8_t*>(aModelBuffer), aBufferSize, &hm);
+  if (err) return err;
+  const unsigned int v[12] = {hm.sample_rate, hm.win_len, hm.win_step, hm.n_input, hm.n_context, hm.n_hidden, hm.n_cell,
+                              hm.n_classes, hm.n_steps, hm.beam_width, hm.space_label, (unsigned int)hm.labels.size()};
+  if (aInfo) memcpy(aInfo, v, sizeof(v));
+  if (aReluClip) *aReluClip = hm.relu_clip;
+  return STT_ERR_OK;
+}
+// One tensor of the parsed model in TF layout ([in, out], fp32): "w1","b1","w2","b2","w3","b3","lstm_kernel","lstm_bias",
+// "w5","b5","w6","b6".  Returns the element count (also when aOut is NULL or aCapacity is too small), negative on error.
+long long STTX_InspectModelTensor(const char* aModelBuffer, unsigned int aBufferSize, const char* aName, float* aOut,
+                                  unsigned long long aCapacity) {
+  sttmodel::HostModel hm;
+  if (sttmodel::load_from_buffer(reinterpret_cast<const uint8_t*>(aModelBuffer), aBufferSize, &hm)) return -1;
+  const std::pair<const char*, const std::vector<float>*> all[] = {
+      {"w1", &hm.w1}, {"b1", &hm.b1}, {"w2", &hm.w2}, {"b2", &hm.b2}, {"w3", &hm.w3}, {"b3", &hm.b3},
+      {"lstm_kernel", &hm.lstm_kernel}, {"lstm_bias", &hm.lstm_bias}, {"w5", &hm.w5}, {"b5", &hm.b5}, {"w6", &hm.w6}, {"b6", &hm.b6}};
+  for (const auto& kv : all)
+    if (!strcmp(kv.first, aName)) {
+      if (aOut && aCapacity >= kv.second->size()) memcpy(aOut, kv.second->data(), kv.second->size() * sizeof(float));
+      return (long long)kv.second->size();
+    }
+  return -2;
+}
+
 int STTX_SpeechToTextBatch(ModelState* aCtx, const short* const* aBuffers, const unsigned int* aBufferSizes,
                            unsigned int aNumBuffers, char** aTranscriptsOut) {
   for (unsigned int i = 0; i < aNumBuffers; ++i) aTranscriptsOut[i] = nullptr;

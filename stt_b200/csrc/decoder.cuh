@@ -43,13 +43,11 @@ constexpr int kMaxWordBytes = 128;
 constexpr int kStateWords = sttscorer::kMaxOrder - 1;
 constexpr int kMaxHotWords = 32;
 constexpr int kCommitRounds = 8;   // candidate rounds (of NT) compacted per scan in phase 6
-constexpr int kHelperWarps = 2;    // LM helper warps of the step kernel (decoder_step_kernel), when it has any
 constexpr int kSelBins = 2048;     // phase 5: bins of the one-pass score histogram
 constexpr int kSelBoundaryCap = 256;  // phase 5: boundary-bin elements resolved by pairwise ranking (more: radix passes)
-// "not computed" marker of Slot::lm_cond (a quiet NaN no LM result can equal): the 8-byte conditional probability is the
-// cache's valid flag AND its payload, so a reader needs no ordering between two loads
+// "not computed" marker of Slot::lm_cond (a quiet NaN no LM result can equal)
 constexpr unsigned long long kLmUnset = 0x7ff8dead5117b200ull;
-constexpr int kFlagHistSelect = 1, kFlagLmHelper = 2;   // DecodeParams::flags
+constexpr int kFlagHistSelect = 1;   // DecodeParams::flags (0: radix passes only -- kept for A/B measurements)
 
 struct Node {            // one surviving prefix (PathTrie node), 32 bytes
   uint32_t parent;       // arena id, kNone for the root
@@ -121,7 +119,7 @@ struct DecodeParams {
   const uint32_t* fst_space_skip;  // [n_states] skip of the state's space arc when that arc ends a word, else kNone
   const uint32_t* ord2wid;         // [n_words] KenLM vocabulary id (0 = <unk>)
   // hot words (ctc_beam_search_decoder.cpp:224-236): vocabulary ids and boosts, snapshotted when the stream starts
-  int flags;             // kFlagHistSelect | kFlagLmHelper
+  int flags;             // kFlagHistSelect
   int n_hot;
   uint32_t hot_id[kMaxHotWords];
   float hot_boost[kMaxHotWords];
@@ -254,29 +252,21 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
                                uint32_t* n_window_out) {
   const sttscorer::ScorerView& v = p.scorer;
   const int order = (int)v.order;
-  // Loads go to L2 (__ldcg): the step kernel's helper warps fill these arrays concurrently (same SM, but an L1 line
-  // fetched earlier must not be believed).  lm_cond is written LAST by whoever evaluates a node, so "cond is set" implies
-  // that the node's state words and meta are in place.
-  const unsigned long long c0bits = __ldcg(reinterpret_cast<const unsigned long long*>(&s.lm_cond[node]));
-  const uint32_t meta0 = __ldcg(&s.lm_meta[node]);   // space nodes: the carried context, see above
+  // lm_cond is both the cache's valid flag (kLmUnset = not computed) and its payload
+  const unsigned long long c0bits = reinterpret_cast<const unsigned long long*>(s.lm_cond)[node];
+  const uint32_t meta0 = s.lm_meta[node];   // space nodes: the carried context, see above
   const double cond0 = __longlong_as_double((long long)c0bits);
-  Node nd;
-  {
-    const uint4* np = reinterpret_cast<const uint4*>(&s.nodes[node]);
-    const uint4 n0 = __ldcg(np), n1 = __ldcg(np + 1);
-    nd.parent = n0.x; nd.chr = n0.y; nd.dict = (int32_t)n0.z; nd.last_space = n0.w;
-    nd.word_id = n1.x; nd.live_slot = n1.y; nd.lm_wid = n1.z; nd.child_mask = n1.w;
-  }
+  const Node nd = s.nodes[node];
   uint32_t stop = stop_hint;
   uint32_t cmeta = kNone;
   uint32_t csw[kStateWords];
   float csb[kStateWords];
   if (stop_hint != kStopUnknown && stop_hint != kNone) {
-    cmeta = __ldcg(&s.lm_meta[stop_hint]);
+    cmeta = s.lm_meta[stop_hint];
 #pragma unroll
     for (int i = 0; i < kStateWords; ++i) {
-      csw[i] = __ldcg(&s.lm_sw[(size_t)stop_hint * kStateWords + i]);
-      csb[i] = __ldcg(&s.lm_sb[(size_t)stop_hint * kStateWords + i]);
+      csw[i] = s.lm_sw[(size_t)stop_hint * kStateWords + i];
+      csb[i] = s.lm_sb[(size_t)stop_hint * kStateWords + i];
     }
   }
   const uint32_t cc = nd.chr;
@@ -289,11 +279,11 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
   if (stop == kStopUnknown) {
     stop = nd.last_space;  // == node when node is itself a space (empty word)
     if (stop != kNone) {
-      cmeta = __ldcg(&s.lm_meta[stop]);
+      cmeta = s.lm_meta[stop];
 #pragma unroll
       for (int i = 0; i < kStateWords; ++i) {
-        csw[i] = __ldcg(&s.lm_sw[(size_t)stop * kStateWords + i]);
-        csb[i] = __ldcg(&s.lm_sb[(size_t)stop * kStateWords + i]);
+        csw[i] = s.lm_sw[(size_t)stop * kStateWords + i];
+        csb[i] = s.lm_sb[(size_t)stop * kStateWords + i];
       }
     }
   }
@@ -308,7 +298,7 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
   }
   if (c0bits != kLmUnset) {
     *word_out = nd.lm_wid;
-    const uint32_t nw = meta0 >> 16;   // statistics only (instrumented builds run without the helper warps)
+    const uint32_t nw = meta0 >> 16;
     *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
     return cond0;
   }
@@ -376,8 +366,7 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
   }
   s.lm_meta[node] = meta;
   if (nd.lm_wid == kNone) s.nodes[node].lm_wid = wid;
-  __threadfence_block();          // state, meta and word id first ...
-  __stcg(&s.lm_cond[node], cond); // ... then the value whose presence says "computed"
+  s.lm_cond[node] = cond;
   *word_out = wid;
   const uint32_t nw = meta >> 16;
   *n_window_out = nw < (uint32_t)order ? nw : (uint32_t)order;
@@ -500,13 +489,11 @@ struct StepSmem {
   uint32_t p0[NC > 0 ? NC : 1], p1[NC > 0 ? NC : 1];
 };
 
-// Launch with NT + 32 * HW threads: threads [0, NT) own the live prefixes; the last HW warps are LM helpers (see the
-// helper loop below).  kInstr compiles in the per-phase clocks and LM counters (bench statistics).  Two CTAs per SM for
-// beams <= 512 (the register budget follows from that), one for the wide instantiation.
-template <int NT, int WC, int NC, bool kInstr, int HW>
-__global__ void __launch_bounds__(NT + 32 * HW, (WC <= 512 ? 2 : 1))
+// kInstr compiles in the per-phase clocks and LM counters (bench statistics).  Two CTAs per SM for beams <= 512 (the
+// register budget follows from that), one for the wide instantiation.
+template <int NT, int WC, int NC, bool kInstr>
+__global__ void __launch_bounds__(NT, (WC <= 512 ? 2 : 1))
 decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
-  constexpr int kHelperThreads = 32 * HW;
   static_assert(NT == 512, "phase 6 assumes 16 warps (kCommitRounds * 16 warp counts scanned by one warp)");
   __shared__ Slot s_slot;   // the slot's pointers and capacities are read all over the step loop
   const int tid = threadIdx.x;
@@ -533,7 +520,6 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
   __shared__ uint32_t s_u[8];
   __shared__ unsigned long long s_ph[8];
   __shared__ unsigned long long s_thresh;   // phase 5: smallest selected key of the boundary bin
-  __shared__ uint32_t s_help[2];            // [0] arena nodes published to the LM helper warps, [1] "launch finished"
   extern __shared__ __align__(16) uint8_t s_dyn[];
   StepSmem<WC, NC>& sm = *reinterpret_cast<StepSmem<WC, NC>*>(s_dyn);
 
@@ -548,41 +534,6 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
     s_u[6] = 0;
     s_u[7] = 0;
     for (int q = 0; q < 8; ++q) s_ph[q] = 0;
-    s_help[0] = arena_count;
-    s_help[1] = 0;
-  }
-  __syncthreads();
-  // ---- LM helper warps.  A prefix's LM term is needed on the critical path the moment the prefix is extended by the
-  //      space label, and evaluating it is a chain of ~10 dependent L2/DRAM round trips (KenLM trie descent) that a
-  //      handful of the NT prefix threads would walk while all the others wait at the next barrier.  The term depends on
-  //      the NODE only, so these warps evaluate every newly created node that completes a dictionary word as soon as
-  //      the commit that created it has been published -- typically a full step before anybody asks -- and leave the
-  //      result in the per-node cache (Slot::lm_cond).  They never join the prefix threads' barrier; a prefix thread
-  //      that finds the cache empty simply evaluates inline as before, so results do not depend on helper timing.
-  if (HW > 0 && tid >= NT) {
-    if (!kInstr && p.has_scorer && p.fst_space_skip != nullptr) {
-      const uint32_t hl = (uint32_t)(tid - NT);
-      uint32_t base = arena_count;   // nodes created by earlier launches are left to the inline path
-      for (;;) {
-        const uint32_t pub = *reinterpret_cast<volatile uint32_t*>(&s_help[0]);
-        if (base < pub) {
-          __threadfence();
-          for (uint32_t id = base + hl; id < pub; id += (uint32_t)kHelperThreads) {
-            const uint4 n1 = __ldcg(reinterpret_cast<const uint4*>(&s.nodes[id]) + 1);   // {word_id|ord, live_slot, lm_wid, child_mask}
-            if (n1.z != kNone) {   // completes a word (set at creation): Scorer::get_log_cond_prob will be asked about it
-              uint32_t w_unused, n_unused;
-              lm_eval_node(s, p, id, kStopUnknown, &w_unused, &n_unused);
-            }
-          }
-          base = pub;
-        } else if (*reinterpret_cast<volatile uint32_t*>(&s_help[1])) {
-          break;
-        } else {
-          __nanosleep(200);
-        }
-      }
-    }
-    return;
   }
   uint32_t* const aux_base = (WC <= 512) ? sm.aux : s.aux;
   uint32_t* const aux_ord[2] = {aux_base, aux_base + WC};
@@ -1205,11 +1156,11 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
               if (pc == (uint32_t)(uint8_t)kRootChar || (int)pc == p.space_id) {
                 meta_init = 0u | (0u << 8) | (1u << 16);  // empty previous word: null context, an OOV inside the window
               } else {
-                meta_init = __ldcg(&s.lm_meta[pnode]);   // written by whoever evaluated the parent (maybe a helper warp)
+                meta_init = s.lm_meta[pnode];
                 const uint32_t len = meta_init == kNone ? 0u : (meta_init & 0xffu);
                 for (uint32_t q = 0; q < len && q < (uint32_t)kStateWords; ++q) {
-                  s.lm_sw[(size_t)id * kStateWords + q] = __ldcg(&s.lm_sw[(size_t)pnode * kStateWords + q]);
-                  s.lm_sb[(size_t)id * kStateWords + q] = __ldcg(&s.lm_sb[(size_t)pnode * kStateWords + q]);
+                  s.lm_sw[(size_t)id * kStateWords + q] = s.lm_sw[(size_t)pnode * kStateWords + q];
+                  s.lm_sb[(size_t)id * kStateWords + q] = s.lm_sb[(size_t)pnode * kStateWords + q];
                 }
               }
             } else if (p.fst_space_skip) {
@@ -1269,10 +1220,6 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
     }
     const uint32_t n_surv = out_base;
     arena_count = s_u[5];
-    if (tid == 0) {   // this commit's nodes (written before the barrier above) may now be read by the LM helper warps
-      __threadfence();
-      *reinterpret_cast<volatile uint32_t*>(&s_help[0]) = arena_count < s.arena_cap ? arena_count : s.arena_cap;
-    }
     ts_count += n_surv;
     if (arena_count > s.arena_cap || ts_count > s.ts_cap) overflow = 1;
     n_live = n_surv;
@@ -1282,7 +1229,6 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
 #undef PHASE_MARK
 
   // ---- store the live list for the next launch / finalize
-  if (tid == 0) *reinterpret_cast<volatile uint32_t*>(&s_help[1]) = 1u;   // helper warps: drain and leave
   main_sync<NT>();
   {
     const LiveList<WC>& L = sm.live[cur];

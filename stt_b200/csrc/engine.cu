@@ -111,7 +111,7 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
 // on its device in a bit mask.  Setting an attribute twice is harmless, so concurrent host threads need no lock.
 enum KernelBit {
   kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
-  kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitDec512, kBitDec512N, kBitDec512I, kBitDec2048, kBitDec2048N, kBitDec2048I
+  kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitDec512, kBitDec512I, kBitDec2048, kBitDec2048I
 };
 template <class K>
 int ensure_smem(std::atomic<uint32_t>* mask, int bit, K kern, int bytes) {
@@ -175,7 +175,7 @@ struct Engine {
   bool lstm_noncoop = false;           // see launch_lstm_pp_inst
   // ---- options, read ONCE when the engine is created (development switches; none is needed in production)
   int opt_lstm_cluster_cap = 8, opt_lstm_pair = 1, opt_lstm_pp_mode = 4, opt_word_ordinals = 1;
-  int opt_dec_flags = sttdec::kFlagHistSelect | sttdec::kFlagLmHelper;
+  int opt_dec_flags = sttdec::kFlagHistSelect;
   int opt_lstm_exact_h = 1;
   bool verbose = false;
 };
@@ -1203,26 +1203,22 @@ int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& i
   cudaStream_t st = b->st;
   CUDA_OK(cudaMemcpyAsync(b->d_inputs, in.data(), sizeof(sttdec::StepInput) * n_slots, cudaMemcpyHostToDevice, st));
   const sttdec::DecodeParams dp = make_decode_params(b, beam);
-  constexpr int NT = 512, HW = sttdec::kHelperWarps;
+  constexpr int NT = 512;
   Engine* e = b->e;
-  // instantiation: beam capacity x {production with LM helper warps, production without, statistics build}
-  const int variant = b->instrument ? 2 : ((e->opt_dec_flags & sttdec::kFlagLmHelper) ? 0 : 1);
-  auto go = [&](auto kern, int bit, size_t smem, int threads) -> int {
+  auto go = [&](auto kern, int bit, size_t smem) -> int {
     if (ensure_smem(&e->cfg_mask, bit, kern, (int)smem)) return -1;
-    kern<<<n_slots, threads, smem, st>>>(b->d_slots, b->d_inputs, dp);
+    kern<<<n_slots, NT, smem, st>>>(b->d_slots, b->d_inputs, dp);
     return 0;
   };
   int rc;
   if (b->beam_cap <= 512) {
     constexpr size_t SM = sizeof(sttdec::StepSmem<512, 3072>);
-    rc = variant == 0   ? go(sttdec::decoder_step_kernel<NT, 512, 3072, false, HW>, kBitDec512, SM, NT + 32 * HW)
-         : variant == 1 ? go(sttdec::decoder_step_kernel<NT, 512, 3072, false, 0>, kBitDec512N, SM, NT)
-                        : go(sttdec::decoder_step_kernel<NT, 512, 3072, true, 0>, kBitDec512I, SM, NT);
+    rc = b->instrument ? go(sttdec::decoder_step_kernel<NT, 512, 3072, true>, kBitDec512I, SM)
+                       : go(sttdec::decoder_step_kernel<NT, 512, 3072, false>, kBitDec512, SM);
   } else if (b->beam_cap <= 2048) {
     constexpr size_t SM = sizeof(sttdec::StepSmem<2048, 0>);
-    rc = variant == 0   ? go(sttdec::decoder_step_kernel<NT, 2048, 0, false, HW>, kBitDec2048, SM, NT + 32 * HW)
-         : variant == 1 ? go(sttdec::decoder_step_kernel<NT, 2048, 0, false, 0>, kBitDec2048N, SM, NT)
-                        : go(sttdec::decoder_step_kernel<NT, 2048, 0, true, 0>, kBitDec2048I, SM, NT);
+    rc = b->instrument ? go(sttdec::decoder_step_kernel<NT, 2048, 0, true>, kBitDec2048I, SM)
+                       : go(sttdec::decoder_step_kernel<NT, 2048, 0, false>, kBitDec2048, SM);
   } else {
     fprintf(stderr, "[stt_b200] beam widths above 2048 are not supported by the shared-memory decoder\n");
     return -1;

@@ -61,6 +61,7 @@ struct Reader {
 
 int load_from_buffer(const uint8_t* data, size_t size, HostModel* m) {
   if (!data || size < 12) return kNoModel;
+  if (looks_like_tflite(data, size)) return load_tflite(data, size, m);
   if (memcmp(data, "STTB200W", 8) != 0) return kFailInitMmap;  // not a model file we can map
   Reader r{data, size};
   r.off = 8;
@@ -84,6 +85,10 @@ int load_from_buffer(const uint8_t* data, size_t size, HostModel* m) {
   // tflitemodelstate.cc:319-329: logits' last dimension must be alphabet size + 1
   if (m->n_classes != m->labels.size() + 1) return kInvalidAlphabet;
   if (!m->n_input || !m->n_hidden || !m->n_cell || !m->n_steps || !m->win_len || !m->win_step || !m->sample_rate)
+    return kInvalidShape;
+  // bound every dimension before sizes are multiplied (a crafted header must not wrap size_t or over-read)
+  if (m->n_input > 4096 || m->n_context > 1024 || m->n_hidden > (1u << 16) || m->n_cell > (1u << 16) ||
+      m->n_classes > (1u << 16) || m->n_steps > 4096 || m->win_len > (1u << 20) || m->win_step > (1u << 20))
     return kInvalidShape;
   const size_t in1 = (size_t)(2 * m->n_context + 1) * m->n_input, H = m->n_hidden, C = m->n_cell, K = m->n_classes;
   r.floats(&m->w1, in1 * H); r.floats(&m->b1, H);

@@ -4,7 +4,7 @@
 // (sample rate, window length/step, beam width, alphabet), the geometry the reference derives from tensor shapes
 // (n_steps, n_context, n_input, n_hidden / n_cell, n_classes) and the fp32 weights of
 // training/coqui_stt_training/deepspeech_model.py:204-263 in TF's own [in, out] layout.
-// A .tflite reader producing the same `HostModel` is SURVEY 8(f) rank 1 ("next").
+// The reference's own container, a .tflite flatbuffer, is read by tflite_reader.cc into the same `HostModel`.
 //
 // Layout (little endian):
 //   char[8] "STTB200W" | u32 version (=1)
@@ -39,7 +39,10 @@ enum LoadError {
   kFailInitMmap = 0x3000,     // STT_ERR_FAIL_INIT_MMAP
 };
 
+// Either container: a TFLite flatbuffer as exported by the reference (tflite_reader.cc) or the native .sttw layout above.
 int load_from_buffer(const uint8_t* data, size_t size, HostModel* out);
+bool looks_like_tflite(const uint8_t* data, size_t size);
+int load_tflite(const uint8_t* data, size_t size, HostModel* out);
 int load_from_file(const char* path, HostModel* out);
 // Alphabet::Deserialize (alphabet.cc:127-169) incl. the space-label detection.
 int deserialize_alphabet(const uint8_t* buf, size_t size, std::vector<std::string>* labels, uint32_t* space_label);

@@ -20,10 +20,22 @@ from conftest import SCORER
 
 pytestmark = pytest.mark.gpu
 
-PROBS_ATOL_SAME_MODE = 2e-3   # SURVEY 8d parity gate 2: GPU vs the restated AM in the same precision mode
-PROBS_ATOL_VS_FP32 = 4e-2     # fp16-operand arithmetic vs fp32 on the x200-calibrated model (measured 2.0e-2, all of it
-                              # operand rounding: profiles/r02_precision_study.json; hybrid int8, the reference's default,
-                              # sits at 0.3-0.56 on the same model)
+# Tolerances.  SURVEY 8d parity gate 2 (|dp| <= 2e-3) is stated for softmax outputs of unit-scale logits and is checked
+# as such on the plain random-init model.  The BENCHMARK model multiplies its output layer by 200 (synth.make_ctc_like,
+# that is what makes a random network emit CTC-like text), so the same hidden-state agreement shows up 200x larger at
+# the logits: there the gates are (measured on B200, profiles/r02_parity_headline.md)
+#   vs the oracle in the SAME precision mode (fp16 operands / fp32 accumulate)  1.0e-2  -> gate 2e-2
+#     (not 0: fp32 accumulation order differs, and a pre-activation that lands on the other side of an fp16 rounding
+#      boundary moves that activation by one fp16 ulp, which 500 recurrent steps and the x200 layer amplify),
+#   vs the fp32 oracle                                                           2.8e-2  -> gate 4e-2
+#     (2.0e-2 of it is operand rounding alone, tools/precision_study.py; the reference's own default arithmetic, TFLite
+#      hybrid int8, is 0.30-0.56 from fp32 on the same model),
+#   frames whose arg-max class differs from fp32                                  0.1 %   -> gate 0.5 %,
+# and transcripts are compared with the fp32 CPU path utterance by utterance (test_headline_transcripts_vs_fp32_cpu_path).
+PROBS_ATOL_UNIT_SCALE = 2e-3
+PROBS_ATOL_SAME_MODE = 2e-2
+PROBS_ATOL_VS_FP32 = 4e-2
+ARGMAX_FLIP_FRAC = 5e-3
 N_SAMPLES = 160000
 B = 256
 
@@ -46,7 +58,32 @@ def headline(tmp_path_factory):
     probs = [b.probs(u) for u in range(B)]
     results = [b.results(u) for u in range(B)]
     assert all(p.shape == (500, 29) for p in probs)
-    return {"model": m, "weights": w, "pcms": pcms, "probs": probs, "results": results}
+    # the same batch through the SAME kernels with the plain (unit-scale) output layer
+    wp = synth.make_weights(n_hidden=2048)
+    ppath = str(tmp_path_factory.mktemp("headline_plain") / "plain.sttw")
+    synth.write_model(ppath, wp, beam_width=500)
+    mp = Model(ppath)
+    bp = mp.createBatch(B, N_SAMPLES)
+    bp.upload(pcms)
+    bp.forward()
+    plain = {u: bp.probs(u) for u in (0, 127, 128, 255)}
+    del bp, mp
+    return {"model": m, "weights": w, "pcms": pcms, "probs": probs, "results": results, "plain_weights": wp,
+            "plain_probs": plain}
+
+
+def test_headline_am_unit_scale_vs_fp32_oracle(oracle, headline):
+    """SURVEY 8d gate 2 on the headline kernel instances (B = 256, T = 500, n_hidden 2048): |dp| <= 2e-3 against the fp32
+    oracle with the plain random-init output layer."""
+    from oracle.am_modes import ModeAM
+    full = ModeAM(headline["plain_weights"], "fp32")
+    worst = 0.0
+    for u, got in headline["plain_probs"].items():
+        _, mfcc = oracle.features_only(headline["pcms"][u])
+        d = float(np.abs(got - full.forward_features(mfcc)).max())
+        print("plain model utt %3d: max|dp| vs fp32 oracle %.3e" % (u, d))
+        worst = max(worst, d)
+    assert worst <= PROBS_ATOL_UNIT_SCALE
 
 
 def test_headline_am_vs_same_precision_oracle(oracle, headline):
@@ -65,13 +102,43 @@ def test_headline_am_vs_same_precision_oracle(oracle, headline):
         assert got.shape == ps.shape == pf.shape
         d_same, d_fp32 = float(np.abs(got - ps).max()), float(np.abs(got - pf).max())
         flips += int((got.argmax(1) != pf.argmax(1)).sum())
-        print("utt %3d: max|dp| vs f16-mode oracle %.3e, vs fp32 oracle %.3e" % (u, d_same, d_fp32))
+        big = pf > 1e-4   # log-domain distance ~ |d logit| (the softmax normaliser moves little)
+        dl = float(np.abs(np.log(got[big]) - np.log(pf[big])).max())
+        print("utt %3d: max|dp| vs f16-mode oracle %.3e, vs fp32 oracle %.3e, max|d ln p| vs fp32 %.3e" % (u, d_same, d_fp32, dl))
         worst_same, worst_fp32 = max(worst_same, d_same), max(worst_fp32, d_fp32)
         np.testing.assert_allclose(got.sum(1), 1.0, rtol=1e-4)
     print("headline AM: worst vs same-mode %.3e (tol %.0e), vs fp32 %.3e (tol %.0e), arg-max flips vs fp32 %d/2000"
           % (worst_same, PROBS_ATOL_SAME_MODE, worst_fp32, PROBS_ATOL_VS_FP32, flips))
     assert worst_same <= PROBS_ATOL_SAME_MODE
     assert worst_fp32 <= PROBS_ATOL_VS_FP32
+    assert flips <= ARGMAX_FLIP_FRAC * 2000
+
+
+def test_headline_transcripts_vs_fp32_cpu_path(ref_decoder, headline, english):
+    """SURVEY 8d gate 3: end-to-end transcripts of the product against the CPU path (oracle MFCC + restated fp32 acoustic
+    model + genuine reference decoder) on the benchmark's full-length utterances.  As many of the 256 as the host gets
+    through in ~4 minutes (all of them on a 128-core box); every divergence is listed."""
+    import time
+    from oracle.cpu_path import CpuPath
+    cp = CpuPath(headline["weights"], SCORER, english, 500)
+    try:
+        done, same, diverged = 0, 0, []
+        t0 = time.time()
+        while done < B and time.time() - t0 < 240:
+            n = min(cp.n_streams, B - done)
+            _, _, res, _ = cp.run(headline["pcms"][done:done + n])
+            for k in range(n):
+                u = done + k
+                if list(res[k][0][1]) == list(headline["results"][u][0][1]):
+                    same += 1
+                else:
+                    diverged.append(u)
+            done += n
+    finally:
+        cp.close()
+    print("end-to-end transcripts identical to the fp32 CPU path: %d/%d (diverged: %s)" % (same, done, diverged))
+    assert done >= 8
+    assert same >= 0.9 * done, "too many transcripts differ from the fp32 CPU path: %s" % diverged
 
 
 def test_headline_rows_equal_single_utterance_path(headline):
