@@ -192,6 +192,9 @@ STT_EXPORT int STTX_BatchSetProbs64(STTX_Batch* b, const double* probs, const in
 STT_EXPORT int STTX_DebugPairLayout(int M, float* out);
 STT_EXPORT int STTX_DebugGemm(int M, int N, int K, const unsigned short* a_f16, const unsigned short* w_f16,
                               const float* bias, int epilogue, float relu_clip, void* out, float* ms);
+/* how many times this stream's device context has garbage-collected its decoder arena (streams are unbounded in length;
+ * PathTrie::remove, path_trie.cpp:192-209, is what bounds the reference's memory) */
+STT_EXPORT long long STTX_StreamArenaCompactions(const StreamingState* aSctx);
 /* Model-file inspection without a device: parses a TFLite flatbuffer (the reference's container,
  * native_client/tflitemodelstate.cc:161-338) or a .sttw file exactly as STT_CreateModel does.  aInfo[12] = sample_rate,
  * win_len, win_step, n_input, n_context, n_hidden, n_cell, n_classes, n_steps, beam_width, space_label, n_labels. */

@@ -55,7 +55,7 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchSetInstrumented", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout", "STTX_InspectModel", "STTX_InspectModelTensor",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout", "STTX_InspectModel", "STTX_InspectModelTensor", "STTX_StreamArenaCompactions",
 ]
 
 
@@ -126,6 +126,8 @@ def lib():
     L.STTX_BatchGetTimings.argtypes = [vp, POINTER(_Timings)]
     L.STTX_BatchKernelLaunches.argtypes = [vp]
     L.STTX_BatchSetInstrumented.argtypes = [vp, c_int]
+    L.STTX_StreamArenaCompactions.argtypes = [vp]
+    L.STTX_StreamArenaCompactions.restype = c_longlong
     L.STTX_InspectModel.argtypes = [c_char_p, c_uint, POINTER(c_uint), POINTER(c_float)]
     L.STTX_InspectModelTensor.argtypes = [c_char_p, c_uint, c_char_p, c_void_p, ctypes.c_ulonglong]
     L.STTX_InspectModelTensor.restype = c_longlong
@@ -275,7 +277,7 @@ class Model(object):
         status = lib().STT_CreateStream(self._impl, byref(ctx))
         if status != 0:
             raise STTError("CreateStream failed with '{}' (0x{:X})".format(_err(status), status))
-        return Stream(ctx)
+        return Stream(ctx, self)
 
     # ---- additive (STTX_*)
     def sttBatch(self, audio_buffers):
@@ -323,8 +325,14 @@ def inspect_model(data):
 class Stream(object):
     """native_client/python/__init__.py:223-383"""
 
-    def __init__(self, native_stream):
+    def __init__(self, native_stream, model=None):
         self._impl = native_stream
+        self._model = model   # the stream's device context belongs to the model: keep it alive as long as the stream
+
+    def arenaCompactions(self):
+        """How often this stream's decoder arena has been garbage-collected so far (STTX_StreamArenaCompactions)."""
+        self._check()
+        return lib().STTX_StreamArenaCompactions(self._impl)
 
     def __del__(self):
         if getattr(self, "_impl", None):

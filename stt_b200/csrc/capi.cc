@@ -8,6 +8,7 @@
 #include <fstream>
 #include <map>
 #include <memory>
+#include <set>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -25,6 +26,7 @@ struct ModelState {  // native_client/modelstate.h:13-27
   unsigned int beam_width_ = 0;
   std::map<std::string, float> hot_words_;
   std::vector<stteng::Batch*> stream_pool;  // idle single-stream device contexts
+  std::set<struct StreamingState*> live_streams;  // streams not yet finished / freed (orphaned by STT_FreeModel)
   bool warned_hot_words = false;
   // device context of the last STTX_SpeechToTextBatch call, kept while the next call fits in it (a context for 256 x 10 s
   // is ~13 GB of device buffers: allocating it per call would cost more than the transcription)
@@ -55,10 +57,13 @@ namespace {
 
 constexpr int kStreamChunk = 512;  // timesteps a stream context can run in one device pass (multiple of n_steps)
 
-int stream_max_seconds() {
-  const char* s = getenv("STT_B200_STREAM_MAX_SECONDS");
-  int v = s ? atoi(s) : 120;
-  return v > 1 ? v : 120;
+// Capacity of a stream's decoder arena in seconds of audio BETWEEN two garbage collections (engine.cu stream_compact):
+// streams are unbounded in length, the arena only has to hold the live trie plus one chunk of new nodes.  16 s at beam
+// 500 is ~45 MB per stream context.
+int stream_arena_seconds() {
+  const char* s = getenv("STT_B200_STREAM_ARENA_SECONDS");
+  int v = s ? atoi(s) : 16;
+  return v >= 12 ? v : 12;   // at least one kStreamChunk (512 timesteps = 10.24 s) of growth
 }
 
 std::string decode_tokens(const sttmodel::HostModel& m, const std::vector<uint32_t>& tokens) {
@@ -146,7 +151,8 @@ int create_model_impl(const uint8_t* data, size_t size, const char* path, ModelS
 int enable_scorer_impl(ModelState* ms, const uint8_t* bytes, size_t n) {
   int err = stteng::engine_set_scorer(ms->engine, bytes, n);
   if (err) return STT_ERR_INVALID_SCORER;  // stt.cc:428-430
-  // live stream contexts snapshot nothing of the scorer: like the reference they see the new one immediately
+  // live streams keep the scorer object they captured at STT_CreateStream (stt.cc:542-547 passes the shared_ptr to
+  // DecoderState::init); streams created from now on get the new one
   return STT_ERR_OK;
 }
 
@@ -158,7 +164,7 @@ stteng::Batch* acquire_stream_ctx(ModelState* ms) {
   }
   const sttmodel::HostModel& m = stteng::engine_model(ms->engine);
   const int max_samples = (kStreamChunk + 40) * (int)m.win_step + (int)m.win_len;
-  const int dec_T = stream_max_seconds() * (int)(m.sample_rate / m.win_step);
+  const int dec_T = stream_arena_seconds() * (int)(m.sample_rate / m.win_step);
   std::string why;
   stteng::Batch* b = stteng::batch_create(ms->engine, 1, max_samples, (int)std::max(1u, ms->beam_width_), dec_T, &why);
   if (!b) fprintf(stderr, "Could not allocate streaming state: %s\n", why.c_str());
@@ -230,6 +236,7 @@ bool stream_drain(StreamingState* s, bool run_partial, bool pad_partial) {
 }
 
 void stream_feed(StreamingState* s, const short* buffer, unsigned int buffer_size) {  // stt.cc:105-128
+  if (!s->model_) return;  // orphaned by STT_FreeModel
   const sttmodel::HostModel& m = stteng::engine_model(s->model_->engine);
   const size_t win = m.win_len, step = m.win_step;
   while (buffer_size > 0) {
@@ -247,6 +254,7 @@ void stream_feed(StreamingState* s, const short* buffer, unsigned int buffer_siz
 }
 
 void stream_flush(StreamingState* s, bool add_zero_mfcc_vectors) {  // stt.cc:236-254
+  if (!s->model_) return;
   const sttmodel::HostModel& m = stteng::engine_model(s->model_->engine);
   // processAudioWindow(audio_buffer_): the partial window, zero padded (tflitemodelstate.cc:343-355); not consumed
   std::vector<int16_t> w(m.win_len, 0);
@@ -266,12 +274,14 @@ std::vector<Decoded> stream_decode(const StreamingState* s, unsigned int num_res
 }
 
 char* stream_decode_text(const StreamingState* s) {  // ModelState::decode, modelstate.cc:32-37
+  if (!s->model_) return nullptr;
   std::vector<Decoded> out = stream_decode(s, 1);
   if (out.empty() || s->failed) return nullptr;
   return dup_string(decode_tokens(stteng::engine_model(s->model_->engine), out[0].tokens));
 }
 
 Metadata* stream_decode_metadata(const StreamingState* s, unsigned int num_results) {
+  if (!s->model_) return nullptr;
   std::vector<Decoded> out = stream_decode(s, num_results);
   if (s->failed) return nullptr;
   Metadata* m = make_metadata(s->model_, out);
@@ -291,7 +301,7 @@ int create_stream_impl(ModelState* ms, StreamingState** retval, bool keep_emissi
     stteng::batch_destroy(ctx->dev);
     const sttmodel::HostModel& m = stteng::engine_model(ms->engine);
     const int max_samples = (kStreamChunk + 40) * (int)m.win_step + (int)m.win_len;
-    const int dec_T = stream_max_seconds() * (int)(m.sample_rate / m.win_step);
+    const int dec_T = stream_arena_seconds() * (int)(m.sample_rate / m.win_step);
     std::string why;
     ctx->dev = stteng::batch_create(ms->engine, 1, max_samples, (int)std::max(1u, ms->beam_width_), dec_T, &why);
     if (!ctx->dev || stteng::batch_stream_reset(ctx->dev, (int)std::max(1u, ms->beam_width_)) != 0) {
@@ -306,6 +316,7 @@ int create_stream_impl(ModelState* ms, StreamingState** retval, bool keep_emissi
     stteng::batch_set_hot_words(ctx->dev, w, bo);
   }
   ctx->audio_buffer_.reserve(stteng::engine_model(ms->engine).win_len);
+  ms->live_streams.insert(ctx.get());
   *retval = ctx.release();
   return STT_ERR_OK;
 }
@@ -338,6 +349,14 @@ int STT_GetModelSampleRate(const ModelState* aCtx) { return (int)stteng::engine_
 
 void STT_FreeModel(ModelState* ctx) {
   if (!ctx) return;
+  // The reference's STT_FreeStream never touches the model, so a client may free the model first: orphan such streams
+  // (their device context dies with the model; STT_FreeStream then only deletes the host-side struct).
+  for (StreamingState* s : ctx->live_streams) {
+    if (s->dev) stteng::batch_destroy(s->dev);
+    s->dev = nullptr;
+    s->model_ = nullptr;
+    s->failed = true;
+  }
   for (stteng::Batch* b : ctx->stream_pool) stteng::batch_destroy(b);
   if (ctx->oneshot) STTX_BatchFree(ctx->oneshot);
   stteng::engine_destroy(ctx->engine);
@@ -462,7 +481,15 @@ Metadata* STT_SpeechToTextWithEmissions(ModelState* aCtx, const short* aBuffer, 
 
 void STT_FreeStream(StreamingState* aSctx) {
   if (!aSctx) return;
-  if (aSctx->dev) aSctx->model_->stream_pool.push_back(aSctx->dev);  // keep the device context for the next stream
+  if (aSctx->model_) {
+    aSctx->model_->live_streams.erase(aSctx);
+    if (aSctx->dev) {
+      stteng::batch_release_scorer(aSctx->dev);            // the stream's handle on its scorer ends with the stream
+      // keep a few device contexts for the next streams (each pins tens of MB); the rest go back to the driver
+      if (aSctx->model_->stream_pool.size() < 4) aSctx->model_->stream_pool.push_back(aSctx->dev);
+      else stteng::batch_destroy(aSctx->dev);
+    }
+  }
   delete aSctx;
 }
 
@@ -634,6 +661,10 @@ long long STTX_InspectModelTensor(const char* aModelBuffer, unsigned int aBuffer
       return (long long)kv.second->size();
     }
   return -2;
+}
+
+long long STTX_StreamArenaCompactions(const StreamingState* aSctx) {
+  return aSctx && aSctx->dev ? stteng::batch_stream_compactions(aSctx->dev) : -1;
 }
 
 int STTX_SpeechToTextBatch(ModelState* aCtx, const short* const* aBuffers, const unsigned int* aBufferSizes,

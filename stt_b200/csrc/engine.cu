@@ -146,6 +146,29 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::Gem
 
 }  // namespace
 
+// ====================================================================================== DeviceScorer
+// The enabled scorer as ONE ref-counted device object, like the reference's std::shared_ptr<Scorer>: the model holds the
+// current one, and every stream / batch decode captures it when its DecoderState is initialised (stt.cc:542-547), so
+// STT_EnableExternalScorer / STT_DisableExternalScorer while a stream is live neither frees tables under a running
+// decode nor mixes dictionary states of two scorers.  Alpha / beta live IN the object (Scorer::reset_params), so
+// STT_SetScorerAlphaBeta reaches the streams that share it, as in the reference.  Freed when the last holder lets go.
+struct DeviceScorer {
+  int device = 0;
+  uint8_t* blob = nullptr;             // the .scorer file verbatim (+16 B pad)
+  size_t blob_bytes = 0;
+  sttscorer::ScorerView view{};        // blob = the device pointer; alpha / beta mutable
+  uint2* fst_state2 = nullptr;         // per state {first arc, label mask}
+  int4* fst_arc4 = nullptr;            // per arc {child dictionary state, its first arc, its label mask, word-ordinal skip} x2
+  uint32_t* fst_space_skip = nullptr;  // word-ordinal tables (decoder.cuh DecodeParams), null when not applicable
+  uint32_t* ord2wid = nullptr;
+  std::vector<uint8_t> vocab_host;     // the vocabulary-hash section, kept on the host for hot-word id lookups
+  ~DeviceScorer() {
+    cudaSetDevice(device);
+    for (void* p : {(void*)blob, (void*)fst_state2, (void*)fst_arc4, (void*)fst_space_skip, (void*)ord2wid})
+      if (p) cudaFree(p);
+  }
+};
+
 // ====================================================================================== Engine
 struct Engine {
   sttmodel::HostModel hm;
@@ -158,14 +181,7 @@ struct Engine {
   // MFCC tables
   sttmfcc::MfccTables tables{};
   std::vector<void*> table_allocs;
-  // scorer
-  bool has_scorer = false;
-  uint8_t* scorer_blob = nullptr;
-  sttscorer::ScorerView scorer_view{};
-  uint2* fst_state2 = nullptr;  // per state {first arc, label mask}
-  int4* fst_arc4 = nullptr;     // per arc {child dictionary state, its first arc, its label mask, word-ordinal skip}
-  uint32_t* fst_space_skip = nullptr;  // word-ordinal tables (decoder.cuh DecodeParams), null when not applicable
-  uint32_t* ord2wid = nullptr;
+  std::shared_ptr<DeviceScorer> scorer;   // the enabled scorer, or null
   // ---- launch state of THIS engine's device (nothing process-wide: one process may drive several GPUs)
   std::atomic<uint32_t> cfg_mask{0};   // KernelBit: kernels whose attributes are set on this device
   std::mutex launch_mu;                // guards the caches below
@@ -181,11 +197,12 @@ struct Engine {
 };
 
 const sttmodel::HostModel& engine_model(const Engine* e) { return e->hm; }
-bool engine_has_scorer(const Engine* e) { return e->has_scorer; }
+bool engine_has_scorer(const Engine* e) { return e->scorer != nullptr; }
 int engine_num_sms(const Engine* e) { return e->num_sms; }
 void engine_set_alpha_beta(Engine* e, float alpha, float beta) {
-  e->scorer_view.alpha = (double)alpha;  // Scorer::reset_params(float, float), scorer.cpp:346-351
-  e->scorer_view.beta = (double)beta;
+  if (!e->scorer) return;
+  e->scorer->view.alpha = (double)alpha;  // Scorer::reset_params(float, float), scorer.cpp:346-351
+  e->scorer->view.beta = (double)beta;
 }
 
 namespace {
@@ -372,18 +389,7 @@ Engine* engine_create(const sttmodel::HostModel& m, std::string* err) {
   return e;
 }
 
-void engine_clear_scorer(Engine* e) {
-  if (e->scorer_blob) cudaFree(e->scorer_blob);
-  if (e->fst_state2) cudaFree(e->fst_state2);
-  if (e->fst_arc4) cudaFree(e->fst_arc4);
-  if (e->fst_space_skip) cudaFree(e->fst_space_skip);
-  if (e->ord2wid) cudaFree(e->ord2wid);
-  e->fst_space_skip = e->ord2wid = nullptr;
-  e->scorer_blob = nullptr;
-  e->fst_state2 = nullptr;
-  e->fst_arc4 = nullptr;
-  e->has_scorer = false;
-}
+void engine_clear_scorer(Engine* e) { e->scorer.reset(); }   // live streams keep the object they captured
 
 void engine_destroy(Engine* e) {
   if (!e) return;
@@ -402,8 +408,8 @@ void engine_destroy(Engine* e) {
 // arc_skip along a word's arcs is its rank among the FST's words in label order.  ord2wid maps that rank to the KenLM
 // vocabulary id of the word's bytes (the same vocab_index the walking path calls).  Anything unexpected -- a cycle, a
 // word that does not end with the space label, more than 2^31 words -- leaves the tables null (walking path).
-void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_t* bytes, std::vector<uint32_t>* skip_out,
-                         std::vector<uint32_t>* space_skip_out) {
+void build_word_ordinals(const Engine* eng, DeviceScorer* e, const sttscorer::ScorerView& v, const uint8_t* bytes,
+                         std::vector<uint32_t>* skip_out, std::vector<uint32_t>* space_skip_out) {
   const int64_t nS = v.fst_nstates, nA = v.fst_narcs;
   if (nS <= 0 || nA <= 0 || v.fst_start < 0 || v.fst_start >= nS) return;
   struct Arc { int32_t il, nx; };
@@ -506,7 +512,7 @@ void build_word_ordinals(Engine* e, const sttscorer::ScorerView& v, const uint8_
   cudaMemcpy(e->ord2wid, o2w.data(), o2w.size() * 4, cudaMemcpyHostToDevice);
   *skip_out = std::move(skip);
   *space_skip_out = std::move(space_skip);
-  if (getenv("STT_B200_VERBOSE")) fprintf(stderr, "[stt_b200] dictionary word ordinals: %llu words\n", (unsigned long long)n_words);
+  if (eng->verbose) fprintf(stderr, "[stt_b200] dictionary word ordinals: %llu words\n", (unsigned long long)n_words);
 }
 
 int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
@@ -518,59 +524,70 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
   int err = sttscorer::parse_scorer(bytes, n, ab, &v);
   if (err) return err;
   if (v.is_utf8) return sttscorer::SCORER_INVALID_TRIE;  // bytes-output mode: SURVEY 8(f) rank 4, not built yet
-  engine_clear_scorer(e);
-  if (cudaMalloc(reinterpret_cast<void**>(&e->scorer_blob), n + 16) != cudaSuccess) return sttscorer::SCORER_UNREADABLE;
-  cudaMemset(e->scorer_blob + n, 0, 16);
-  if (cudaMemcpy(e->scorer_blob, bytes, n, cudaMemcpyHostToDevice) != cudaSuccess) return sttscorer::SCORER_UNREADABLE;
+  // Everything is parsed, validated and uploaded into a NEW object; the engine's current scorer is replaced only when
+  // all of it has succeeded (a failed STT_EnableExternalScorer leaves the old scorer enabled, stt.cc:428-432).
+  std::shared_ptr<DeviceScorer> ds = std::make_shared<DeviceScorer>();
+  ds->device = e->device;
+  if (v.fst_nstates <= 0 || v.fst_start < 0 || v.fst_start >= v.fst_nstates || v.fst_narcs < 0) return sttscorer::SCORER_INVALID_TRIE;
   // Pre-digest the dictionary FST for the decoder (semantics of PathTrie::get_path_trie, path_trie.cpp:60-88):
   // per state the set of labels with an outgoing arc, per arc the child's dictionary state, i.e. Start() when the
   // arc's target is final ("restart spell checker at the start state"), else the target.
-  {
-    v.blob = bytes;  // host view for the preprocessing
-    std::vector<uint2> st2((size_t)v.fst_nstates);
-    std::vector<int2> ar2((size_t)v.fst_narcs);
-    for (int64_t q = 0; q < v.fst_nstates; ++q) {
-      const uint8_t* srec = bytes + v.fst_states_off + (uint64_t)q * 20;
-      uint32_t pos, narcs;
-      memcpy(&pos, srec + 4, 4);
-      memcpy(&narcs, srec + 8, 4);
-      uint32_t mask = 0;
-      for (uint32_t a = 0; a < narcs; ++a) {
-        const uint8_t* arc = bytes + v.fst_arcs_off + (uint64_t)(pos + a) * 16;
-        int32_t il, nx;
-        memcpy(&il, arc, 4);
-        memcpy(&nx, arc + 12, 4);
-        if (il >= 1 && il <= 32) mask |= 1u << (il - 1);
-        if (a > 0) {
-          int32_t prev;
-          memcpy(&prev, arc - 16, 4);
-          if (prev >= il) return sttscorer::SCORER_INVALID_TRIE;  // SortedMatcher needs ilabel-sorted, deterministic arcs
-        }
-        if (nx < 0 || nx >= v.fst_nstates || (uint64_t)pos + a >= (uint64_t)v.fst_narcs) return sttscorer::SCORER_INVALID_TRIE;
-        const bool fin = sttscorer::fst_is_final(v, nx);
-        ar2[pos + a] = make_int2(il, fin ? (int32_t)v.fst_start : nx);
+  v.blob = bytes;  // host view for the preprocessing
+  std::vector<uint2> st2((size_t)v.fst_nstates);
+  std::vector<int2> ar2((size_t)v.fst_narcs);
+  for (int64_t q = 0; q < v.fst_nstates; ++q) {
+    const uint8_t* srec = bytes + v.fst_states_off + (uint64_t)q * 20;
+    uint32_t pos, narcs;
+    memcpy(&pos, srec + 4, 4);
+    memcpy(&narcs, srec + 8, 4);
+    if ((uint64_t)pos + narcs > (uint64_t)v.fst_narcs) return sttscorer::SCORER_INVALID_TRIE;  // before any arc is read
+    uint32_t mask = 0;
+    for (uint32_t a = 0; a < narcs; ++a) {
+      const uint8_t* arc = bytes + v.fst_arcs_off + (uint64_t)(pos + a) * 16;
+      int32_t il, nx;
+      memcpy(&il, arc, 4);
+      memcpy(&nx, arc + 12, 4);
+      if (il >= 1 && il <= 32) mask |= 1u << (il - 1);
+      if (a > 0) {
+        int32_t prev;
+        memcpy(&prev, arc - 16, 4);
+        if (prev >= il) return sttscorer::SCORER_INVALID_TRIE;  // SortedMatcher needs ilabel-sorted, deterministic arcs
       }
-      st2[(size_t)q] = make_uint2(pos, mask);
+      if (nx < 0 || nx >= v.fst_nstates) return sttscorer::SCORER_INVALID_TRIE;
+      const bool fin = sttscorer::fst_is_final(v, nx);
+      ar2[pos + a] = make_int2(il, fin ? (int32_t)v.fst_start : nx);
     }
-    std::vector<uint32_t> skip, space_skip;
-    build_word_ordinals(e, v, bytes, &skip, &space_skip);
-    // two 16-byte words per arc: {child state, child's first arc, child's label mask, ordinal skip} and
-    // {ordinal skip of the CHILD state's space arc (or none), -, -, -}
-    std::vector<int4> ar4(2 * ar2.size());
-    for (size_t i = 0; i < ar2.size(); ++i) {
-      const uint2 cs = st2[(size_t)ar2[i].y];
-      ar4[2 * i] = make_int4(ar2[i].y, (int)cs.x, (int)cs.y, skip.empty() ? 0 : (int)skip[i]);
-      ar4[2 * i + 1] = make_int4(space_skip.empty() ? -1 : (int)space_skip[(size_t)ar2[i].y], 0, 0, 0);
-    }
-    if (cudaMalloc(reinterpret_cast<void**>(&e->fst_state2), std::max<size_t>(st2.size(), 1) * sizeof(uint2)) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&e->fst_arc4), std::max<size_t>(ar4.size(), 1) * sizeof(int4)) != cudaSuccess)
-      return sttscorer::SCORER_UNREADABLE;
-    cudaMemcpy(e->fst_state2, st2.data(), st2.size() * sizeof(uint2), cudaMemcpyHostToDevice);
-    cudaMemcpy(e->fst_arc4, ar4.data(), ar4.size() * sizeof(int4), cudaMemcpyHostToDevice);
+    st2[(size_t)q] = make_uint2(pos, mask);
   }
-  v.blob = e->scorer_blob;
-  e->scorer_view = v;
-  e->has_scorer = true;
+  std::vector<uint32_t> skip, space_skip;
+  build_word_ordinals(e, ds.get(), v, bytes, &skip, &space_skip);
+  // two 16-byte words per arc: {child state, child's first arc, child's label mask, ordinal skip} and
+  // {ordinal skip of the CHILD state's space arc (or none), -, -, -}
+  std::vector<int4> ar4(2 * ar2.size());
+  for (size_t i = 0; i < ar2.size(); ++i) {
+    const uint2 cs = st2[(size_t)ar2[i].y];
+    ar4[2 * i] = make_int4(ar2[i].y, (int)cs.x, (int)cs.y, skip.empty() ? 0 : (int)skip[i]);
+    ar4[2 * i + 1] = make_int4(space_skip.empty() ? -1 : (int)space_skip[(size_t)ar2[i].y], 0, 0, 0);
+  }
+  if (cudaMalloc(reinterpret_cast<void**>(&ds->blob), n + 16) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&ds->fst_state2), std::max<size_t>(st2.size(), 1) * sizeof(uint2)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&ds->fst_arc4), std::max<size_t>(ar4.size(), 1) * sizeof(int4)) != cudaSuccess) {
+    cudaGetLastError();
+    return sttscorer::SCORER_UNREADABLE;
+  }
+  if (cudaMemset(ds->blob + n, 0, 16) != cudaSuccess || cudaMemcpy(ds->blob, bytes, n, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ds->fst_state2, st2.data(), st2.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ds->fst_arc4, ar4.data(), ar4.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    return sttscorer::SCORER_UNREADABLE;
+  }
+  ds->blob_bytes = n;
+  const size_t vocab_end = std::min<size_t>(n, (size_t)(v.vocab_off + v.vocab_count * 8 + 16));
+  ds->vocab_host.assign(bytes, bytes + vocab_end);
+  ds->vocab_host.resize(vocab_end + 16, 0);
+  v.blob = ds->blob;
+  ds->view = v;
+  e->scorer = std::move(ds);   // the previous object lives on in the streams that captured it
   return 0;
 }
 
@@ -622,8 +639,11 @@ struct Batch {
   int16_t* d_win = nullptr;
   sttmfcc::FrameJob* d_jobs = nullptr;
   int last_run_T = 0;
+  uint32_t stream_arena_count = 1, stream_ts_count = 1;   // host mirror of the stream slot's arena / timestep-tree fill
+  long long stream_compactions = 0;
   StageTimes times;
   long long launches = 0;
+  std::shared_ptr<DeviceScorer> scorer;   // captured by decoder_reset: the scorer this decode / stream runs with
   bool instrument = false;   // decoder statistics build (per-phase clocks, LM counters); bench.py asks for it once
 };
 
@@ -1169,14 +1189,15 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
   dp.n_classes = e->hm.n_classes;
   dp.beam = beam;
   dp.space_id = (int)e->hm.space_label;
-  dp.has_scorer = e->has_scorer ? 1 : 0;
-  if (e->has_scorer) dp.scorer = e->scorer_view;
-  dp.fst_state2 = e->fst_state2;
-  dp.fst_arc4 = e->fst_arc4;
-  dp.fst_space_skip = e->opt_word_ordinals ? e->fst_space_skip : nullptr;
+  const DeviceScorer* sc = b->scorer.get();   // the one captured when this decode's state was initialised
+  dp.has_scorer = sc ? 1 : 0;
+  if (sc) dp.scorer = sc->view;               // alpha / beta as they are NOW (shared object, scorer.cpp:346-351)
+  dp.fst_state2 = sc ? sc->fst_state2 : nullptr;
+  dp.fst_arc4 = sc ? sc->fst_arc4 : nullptr;
+  dp.fst_space_skip = (sc && e->opt_word_ordinals) ? sc->fst_space_skip : nullptr;
   dp.flags = e->opt_dec_flags;
-  dp.ord2wid = dp.fst_space_skip ? e->ord2wid : nullptr;
-  dp.n_hot = e->has_scorer ? (int)std::min<size_t>(b->hot_ids.size(), sttdec::kMaxHotWords) : 0;
+  dp.ord2wid = dp.fst_space_skip ? sc->ord2wid : nullptr;
+  dp.n_hot = sc ? (int)std::min<size_t>(b->hot_ids.size(), sttdec::kMaxHotWords) : 0;
   for (int h = 0; h < dp.n_hot; ++h) {
     dp.hot_id[h] = b->hot_ids[h];
     dp.hot_boost[h] = b->hot_boosts[h];
@@ -1186,7 +1207,8 @@ sttdec::DecodeParams make_decode_params(const Batch* b, int beam) {
 
 int decoder_reset(Batch* b, int n_slots) {
   cudaStream_t st = b->st;
-  const int32_t fst_start = b->e->has_scorer ? (int32_t)b->e->scorer_view.fst_start : 0;
+  b->scorer = b->e->scorer;   // DecoderState::init takes its own handle on the scorer (stt.cc:542-547)
+  const int32_t fst_start = b->scorer ? (int32_t)b->scorer->view.fst_start : 0;
   // (parent, label) hash tables are never cleared between decodes: entries carry a generation (decoder.cuh ht_insert)
   if (++b->ht_gen > 255u) {
     for (int u = 0; u < b->B_cap; ++u)
@@ -1300,13 +1322,10 @@ int batch_set_hot_words(Batch* b, const std::vector<std::string>& words, const s
   b->hot_ids.clear();
   b->hot_boosts.clear();
   const Engine* e = b->e;
-  if (!e->has_scorer) return 0;
-  std::vector<uint8_t> host;  // the vocabulary hashes live at the start of the blob; read them back once
-  const sttscorer::ScorerView& dv = e->scorer_view;
-  host.resize(dv.vocab_off + dv.vocab_count * 8 + 16);
-  CUDA_OK(cudaMemcpy(host.data(), e->scorer_blob, host.size(), cudaMemcpyDeviceToHost));
-  sttscorer::ScorerView hv = dv;
-  hv.blob = host.data();
+  const DeviceScorer* sc = e->scorer.get();   // the scorer the coming decode will capture
+  if (!sc) return 0;
+  sttscorer::ScorerView hv = sc->view;
+  hv.blob = sc->vocab_host.data();            // the vocabulary hashes sit at the start of the file
   for (size_t i = 0; i < words.size(); ++i) {
     const uint32_t id = sttscorer::vocab_index(hv, reinterpret_cast<const uint8_t*>(words[i].data()), (uint32_t)words[i].size());
     if (id != 0) {
@@ -1470,6 +1489,8 @@ int batch_stream_reset(Batch* b, int beam) {
   CUDA_OK(cudaMemsetAsync(b->d_c, 0, (size_t)e->Cp * 4, st));
   CUDA_OK(cudaMemsetAsync(b->d_h, 0, (size_t)e->Cp * 4, st));
   if (decoder_reset(b, 1)) return -1;
+  b->stream_arena_count = 1;
+  b->stream_ts_count = 1;
   // mfcc_buffer_ starts with n_context literal-zero frames (stt.cc:533)
   b->stream_frames = e->hm.n_context;
   CUDA_OK(cudaStreamSynchronize(st));
@@ -1507,6 +1528,124 @@ int batch_stream_push_windows(Batch* b, const int16_t* windows, const int* n_val
   return 0;
 }
 
+namespace {
+
+uint32_t host_ht_hash(unsigned long long k) {   // decoder.cuh ht_hash
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+// Garbage collection of a stream's decoder arena.  The reference's trie never holds more than the live prefixes and
+// their ancestors: PathTrie::remove (path_trie.cpp:192-209) deletes a pruned node that has no children and walks up
+// its chain of dead parents, so memory is O(beam x transcript length) however long the stream runs.  The device arena
+// is append-only while a chunk is being decoded; between chunks, when the next chunk might not fit, the slot is
+// brought to the host, everything unreachable from the live list is dropped (nodes, their LM cache rows, timestep-tree
+// nodes), ids are renumbered in creation order (a parent still precedes its children), every node's created-children
+// mask and the (parent, label) hash table are rebuilt from the survivors, and the slot goes back.  A dropped node that
+// re-enters the beam later is created afresh -- exactly what the reference does after having deleted it.
+int stream_compact(Batch* b) {
+  using sttdec::kNone;
+  cudaStream_t st = b->st;
+  CUDA_OK(cudaStreamSynchronize(st));
+  sttdec::Slot& sl = b->h_slots[0];
+  uint32_t sc[16];
+  CUDA_OK(cudaMemcpy(sc, sl.scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+  const uint32_t n_live = sc[0], A = std::min(sc[2], sl.arena_cap), TS = std::min(sc[3], sl.ts_cap);
+  const int SW = sttdec::kStateWords;
+  std::vector<sttdec::Node> nodes(A);
+  std::vector<double> lmc(A);
+  std::vector<uint32_t> lmsw((size_t)A * SW), lmm(A), live_node(n_live), live_ts(n_live);
+  std::vector<float> lmsb((size_t)A * SW);
+  std::vector<uint2> tst(TS);
+  CUDA_OK(cudaMemcpy(nodes.data(), sl.nodes, sizeof(sttdec::Node) * A, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(lmc.data(), sl.lm_cond, 8ull * A, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(lmsw.data(), sl.lm_sw, 4ull * A * SW, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(lmsb.data(), sl.lm_sb, 4ull * A * SW, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(lmm.data(), sl.lm_meta, 4ull * A, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(tst.data(), sl.ts_tree, 8ull * TS, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(live_node.data(), sl.node, 4ull * n_live, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(live_ts.data(), sl.ts, 4ull * n_live, cudaMemcpyDeviceToHost));
+  // ---- mark what the live prefixes reach
+  std::vector<uint8_t> keep(A, 0), keep_ts(TS, 0);
+  keep[0] = 1;
+  if (TS) keep_ts[0] = 1;
+  for (uint32_t i = 0; i < n_live; ++i) {
+    for (uint32_t id = live_node[i]; id != kNone && id < A && !keep[id]; id = nodes[id].parent) keep[id] = 1;
+    for (uint32_t t = live_ts[i]; t != kNone && t < TS && !keep_ts[t]; t = tst[t].x) keep_ts[t] = 1;
+  }
+  std::vector<uint32_t> map(A, kNone), map_ts(TS, kNone);
+  uint32_t A2 = 0, TS2 = 0;
+  for (uint32_t id = 0; id < A; ++id)
+    if (keep[id]) map[id] = A2++;
+  for (uint32_t t = 0; t < TS; ++t)
+    if (keep_ts[t]) map_ts[t] = TS2++;
+  // ---- rewrite (in place, front to back: map[id] <= id)
+  for (uint32_t id = 0; id < A; ++id) {
+    if (!keep[id]) continue;
+    sttdec::Node n = nodes[id];
+    n.parent = n.parent == kNone ? kNone : map[n.parent];
+    n.last_space = n.last_space == kNone ? kNone : map[n.last_space];
+    n.live_slot = kNone;
+    n.child_mask = 0;
+    const uint32_t d = map[id];
+    nodes[d] = n;
+    lmc[d] = lmc[id];
+    lmm[d] = lmm[id];
+    for (int q = 0; q < SW; ++q) {
+      lmsw[(size_t)d * SW + q] = lmsw[(size_t)id * SW + q];
+      lmsb[(size_t)d * SW + q] = lmsb[(size_t)id * SW + q];
+    }
+  }
+  for (uint32_t t = 0; t < TS; ++t) {
+    if (!keep_ts[t]) continue;
+    uint2 v = tst[t];
+    v.x = v.x == kNone ? kNone : map_ts[v.x];
+    tst[map_ts[t]] = v;
+  }
+  const uint32_t gen = sl.ht_gen ? sl.ht_gen : b->ht_gen;
+  std::vector<unsigned long long> ht((size_t)sl.ht_mask + 1, 0ull);
+  for (uint32_t d = 1; d < A2; ++d) {
+    const sttdec::Node& n = nodes[d];
+    if (n.parent == kNone) continue;
+    nodes[n.parent].child_mask |= 1u << (n.chr & 31u);
+    const unsigned long long w = ((unsigned long long)gen << 56) | ((unsigned long long)(n.parent & 0xffffffu) << 32) |
+                                 ((unsigned long long)(n.chr & 0xffu) << 24) | (unsigned long long)(d & 0xffffffu);
+    uint32_t h = host_ht_hash(w >> 24) & sl.ht_mask;
+    while (ht[h] != 0) h = (h + 1) & sl.ht_mask;   // any placement on the probe path before an empty slot is findable
+    ht[h] = w;
+  }
+  for (uint32_t i = 0; i < n_live; ++i) {
+    live_node[i] = map[live_node[i]];
+    nodes[live_node[i]].live_slot = i;
+    if (live_ts[i] != kNone) live_ts[i] = map_ts[live_ts[i]];
+  }
+  // ---- back to the device
+  CUDA_OK(cudaMemcpy(sl.nodes, nodes.data(), sizeof(sttdec::Node) * A2, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sl.lm_cond, lmc.data(), 8ull * A2, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sl.lm_sw, lmsw.data(), 4ull * A2 * SW, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sl.lm_sb, lmsb.data(), 4ull * A2 * SW, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sl.lm_meta, lmm.data(), 4ull * A2, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sl.ts_tree, tst.data(), 8ull * TS2, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sl.ht, ht.data(), 8ull * ht.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sl.node, live_node.data(), 4ull * n_live, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(sl.ts, live_ts.data(), 4ull * n_live, cudaMemcpyHostToDevice));
+  sc[2] = A2;
+  sc[3] = TS2;
+  CUDA_OK(cudaMemcpy(sl.scalars, sc, sizeof(sc), cudaMemcpyHostToDevice));
+  if (b->e->verbose)
+    fprintf(stderr, "[stt_b200] stream arena compacted: %u -> %u nodes, %u -> %u timestep nodes\n", A, A2, TS, TS2);
+  b->stream_arena_count = A2;
+  b->stream_ts_count = TS2;
+  ++b->stream_compactions;
+  return 0;
+}
+
+}  // namespace
+
+long long batch_stream_compactions(const Batch* b) { return b->stream_compactions; }
+
 int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_probs) {
   cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   (void)keep_last_probs;
@@ -1515,6 +1654,19 @@ int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_p
   const int need = n_timesteps + 2 * (int)m.n_context;
   if (n_timesteps < 1 || n_timesteps > b->T_cap || b->stream_frames < need) return -2;
   cudaStream_t st = b->st;
+  {
+    // every step appends at most `beam` arena nodes and `beam` timestep-tree nodes: make room before the chunk runs
+    const unsigned long long grow = (unsigned long long)b->cur_beam * (unsigned long long)n_timesteps;
+    const sttdec::Slot& sl = b->h_slots[0];
+    if (b->stream_arena_count + grow > sl.arena_cap || b->stream_ts_count + grow > sl.ts_cap) {
+      if (stream_compact(b)) return -1;
+      if (b->stream_arena_count + grow > sl.arena_cap || b->stream_ts_count + grow > sl.ts_cap) {
+        fprintf(stderr, "[stt_b200] stream decoder arena too small even after compaction (%u live-trie nodes of %u): raise "
+                        "STT_B200_STREAM_ARENA_SECONDS\n", b->stream_arena_count, sl.arena_cap);
+        return -3;
+      }
+    }
+  }
   // carried LSTM state: h (fp32) -> block 0 of h_all (fp16); c stays in d_c
   f32_to_f16_kernel<<<(e->Cp + 255) / 256, 256, 0, st>>>(b->d_h, b->d_hall, (size_t)e->Cp);
   b->launches += 1;
@@ -1555,9 +1707,11 @@ int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_p
   uint32_t sc[8];
   CUDA_OK(cudaMemcpy(sc, b->h_slots[0].scalars, sizeof(sc), cudaMemcpyDeviceToHost));
   if (sc[6]) {
-    fprintf(stderr, "[stt_b200] stream decoder capacity exceeded (raise STT_B200_STREAM_MAX_SECONDS)\n");
+    fprintf(stderr, "[stt_b200] stream decoder capacity exceeded\n");
     return -3;
   }
+  b->stream_arena_count = sc[2];
+  b->stream_ts_count = sc[3];
   return 0;
 }
 
@@ -1572,6 +1726,10 @@ int batch_stream_decode(Batch* b, int num_results, std::vector<Decoded>* out) {
 }
 
 int batch_stream_frames(const Batch* b) { return b->stream_frames; }
+void batch_release_scorer(Batch* b) {
+  if (b->st) cudaStreamSynchronize(b->st);
+  b->scorer.reset();
+}
 
 int batch_stream_last_probs(Batch* b, std::vector<double>* out, int* n_rows) {
   cudaSetDevice(b->e->device);  // CUDA's current device is per host thread

@@ -63,6 +63,8 @@ int batch_stream_push_windows(Batch* b, const int16_t* windows, const int* n_val
 int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_probs);  // one `infer` + DecoderState::next
 int batch_stream_decode(Batch* b, int num_results, std::vector<Decoded>* out);
 int batch_stream_frames(const Batch* b);
+void batch_release_scorer(Batch* b);
+long long batch_stream_compactions(const Batch* b);                         // arena garbage collections of this context so far                                        // drop the scorer captured by the last reset
 int batch_stream_last_probs(Batch* b, std::vector<double>* out, int* n_rows);
 
 // raw GEMM hook for the kernel unit tests: C = epi(A[M,K] * W[N,K]^T + bias)

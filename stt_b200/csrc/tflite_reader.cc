@@ -77,7 +77,15 @@ struct Fb {
     const size_t f = field(t, id);
     return f ? rd<T>(f) : dflt;
   }
-  uint32_t vec_len(size_t v) { return v ? rd<uint32_t>(v) : 0; }
+  uint32_t vec_len(size_t v) {
+    if (!v) return 0;
+    const uint32_t len = rd<uint32_t>(v);
+    if (len > n) {  // even one byte per element would not fit: corrupt length
+      ok = false;
+      return 0;
+    }
+    return len;
+  }
   // element position of a vector of scalars / inline structs
   size_t vec_at(size_t v, uint32_t i, size_t elem) {
     const size_t pos = v + 4 + (size_t)i * elem;
