@@ -388,6 +388,17 @@ def main():
             else:
                 cmp_probs, cmp_res = gpu_probs[:n_s], gpu_res[:n_s]
             same_e2e = sum(int(list(ref_res[u][0][1]) == list(cmp_res[u][1])) for u in range(n_s))
+
+            def edits(a, b):   # Levenshtein distance in labels
+                prev = list(range(len(b) + 1))
+                for i, x in enumerate(a, 1):
+                    cur = [i]
+                    for j, y in enumerate(b, 1):
+                        cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (x != y)))
+                    prev = cur
+                return prev[-1]
+            n_edits = sum(edits(list(ref_res[u][0][1]), list(cmp_res[u][1])) for u in range(n_s))
+            n_labels = sum(len(ref_res[u][0][1]) for u in range(n_s))
             dmax = max(float(np.abs(cmp_probs[u] - ref_probs[u]).max()) for u in range(n_s))
             flips = sum(int((cmp_probs[u].argmax(1) != ref_probs[u].argmax(1)).sum()) for u in range(n_s))
             # gate 2 in the SAME precision mode (fp16 operands, fp32 accumulate) on two utterances
@@ -402,8 +413,9 @@ def main():
                 "decoder_identical_to_reference_on_gpu_probs": "%d/%d" % (same_dec, B),
                 "decoder_clip_seconds": args.seconds, "reference_decoder_wall_s": ref_dec_s,
                 "transcripts_identical_to_cpu_fp32_path": "%d/%d" % (same_e2e, n_s),
+                "label_error_rate_vs_cpu_fp32_path": n_edits / float(max(1, n_labels)), "label_edits": "%d/%d" % (n_edits, n_labels),
                 "parity_clip_seconds": cpu_seconds,
-                "max_abs_dprob_vs_same_precision_oracle": dsame, "tolerance_same_precision": 2e-3,
+                "max_abs_dprob_vs_same_precision_oracle": dsame, "tolerance_same_precision_x200_model": 2e-2,
                 "max_abs_dprob_vs_restated_fp32_am": dmax, "argmax_flips_vs_fp32": "%d/%d" % (flips, n_s * cmp_probs[0].shape[0]),
                 "note": "fp16-operand arithmetic vs fp32 on this x200-calibrated output layer is 2e-2, all of it operand "
                         "rounding (profiles/r02_precision_study.json); the reference's default export arithmetic (TFLite "

@@ -595,6 +595,7 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
 struct Batch {
   Engine* e = nullptr;
   int B_cap = 0, S_cap = 0, T_cap = 0, beam_cap = 0, dec_T_cap = 0, max_results = 0;
+  int out_tok_cap = 0;         // tokens per result the output blocks hold (a stream's transcript may outgrow its arena)
   int B = 0, T_max = 0;
   uint32_t ht_gen = 0;  // generation of the decoder hash tables (decoder_reset)
   std::vector<int> T;  // timesteps per utterance
@@ -707,7 +708,8 @@ int alloc_slots(Batch* b) {
   CUDA_OK(cudaMemcpy(b->d_slots, b->h_slots.data(), sizeof(sttdec::Slot) * b->B_cap, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_inputs), sizeof(sttdec::StepInput) * b->B_cap));
   // outputs: per utterance [n_results i32][pad][confidence f64 x R][n_tokens i32 x R][tokens u32 x R*Tm][timesteps ...]
-  const int R = b->max_results, Tm = b->dec_T_cap;
+  b->out_tok_cap = b->dec_T_cap;
+  const int R = b->max_results, Tm = b->out_tok_cap;
   size_t per = 0;
   per = align_up(per + 8, 8);
   const size_t o_conf = per; per += 8ull * R;
@@ -1259,15 +1261,16 @@ int decoder_finalize(Batch* b, int n_slots, int beam, int num_results) {
   return 0;
 }
 
-int ensure_results_capacity(Batch* b, int num_results) {
-  if (num_results <= b->max_results) return 0;
+int ensure_results_capacity(Batch* b, int num_results, int tok_cap = 0) {
+  if (num_results <= b->max_results && tok_cap <= b->out_tok_cap) return 0;
   // re-create output buffers with a larger result count
   cudaStreamSynchronize(b->st);
   cudaFree(b->d_out_mem); b->d_out_mem = nullptr;
   cudaFreeHost(b->h_out_mem); b->h_out_mem = nullptr;
   cudaFree(b->d_finals); b->d_finals = nullptr;
-  b->max_results = num_results;
-  const int R = b->max_results, Tm = b->dec_T_cap;
+  b->max_results = std::max(b->max_results, num_results);
+  b->out_tok_cap = std::max(b->out_tok_cap, tok_cap);
+  const int R = b->max_results, Tm = b->out_tok_cap;
   size_t per = 8;
   const size_t o_conf = per; per += 8ull * R;
   const size_t o_nt = per; per += 4ull * R;
@@ -1292,7 +1295,7 @@ int ensure_results_capacity(Batch* b, int num_results) {
 
 // parse one utterance's result block (host copy)
 void parse_results(const Batch* b, const uint8_t* base, std::vector<Decoded>* out) {
-  const int R = b->max_results, Tm = b->dec_T_cap;
+  const int R = b->max_results, Tm = b->out_tok_cap;
   size_t per = 8;
   const size_t o_conf = per; per += 8ull * R;
   const size_t o_nt = per; per += 4ull * R;
@@ -1718,9 +1721,21 @@ int batch_stream_run(Batch* b, int n_timesteps, int n_pad_rows, bool keep_last_p
 int batch_stream_decode(Batch* b, int num_results, std::vector<Decoded>* out) {
   cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (ensure_results_capacity(b, num_results)) return -1;
-  if (decoder_finalize(b, 1, b->cur_beam, num_results)) return -1;
-  CUDA_OK(cudaMemcpyAsync(b->h_out_mem, b->d_out_mem, b->out_bytes_per_utt, cudaMemcpyDeviceToHost, b->st));
-  CUDA_OK(cudaStreamSynchronize(b->st));
+  for (;;) {
+    if (decoder_finalize(b, 1, b->cur_beam, num_results)) return -1;
+    CUDA_OK(cudaMemcpyAsync(b->h_out_mem, b->d_out_mem, b->out_bytes_per_utt, cudaMemcpyDeviceToHost, b->st));
+    CUDA_OK(cudaStreamSynchronize(b->st));
+    // A stream is unbounded, so its transcript can outgrow the output block sized when the stream was created: the
+    // finalize kernel reports the full token counts, the block grows and the (const) finalize runs again.
+    const int n = *reinterpret_cast<const int*>(b->h_out_mem);
+    const int* nt = reinterpret_cast<const int*>(b->h_out_mem + 8 + 8ull * b->max_results);
+    int longest = 0;
+    for (int r = 0; r < n; ++r) longest = std::max(longest, nt[r]);
+    if (longest <= b->out_tok_cap) break;
+    int cap = b->out_tok_cap;
+    while (cap < longest) cap *= 2;
+    if (ensure_results_capacity(b, num_results, cap)) return -1;
+  }
   parse_results(b, b->h_out_mem, out);
   return 0;
 }

@@ -104,8 +104,8 @@ def test_stream_keeps_its_scorer(ctc_model, tmp_path):
         if meddle is broken:
             assert m.stt(pcm) == base                      # the old scorer is still the enabled one
         if meddle is disable:
-            with pytest.raises(STTError):                   # STT_ERR_SCORER_NOT_ENABLED
-                m.setScorerAlphaBeta(1.0, 1.0)
+            # the reference binding returns the code instead of raising (native_client/python/__init__.py:161-174)
+            assert m.setScorerAlphaBeta(1.0, 1.0) == 0x2004   # STT_ERR_SCORER_NOT_ENABLED (coqui-stt.h)
             assert m.stt(pcm) != base                      # new streams decode without a scorer
         if meddle is other:
             assert m.stt(pcm) != base                      # new streams use the new scorer
