@@ -12,7 +12,7 @@ BUILD     := build
 
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh) include/stt_capi.h
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean variant
 CLI       := stt_b200/stt
 all: $(OUT) $(CLI)
 
@@ -29,6 +29,12 @@ $(BUILD)/%.o: $(SRC)/%.cc $(HDRS)
 
 $(OUT): $(BUILD)/engine.o $(BUILD)/capi.o $(BUILD)/model_file.o $(BUILD)/tflite_reader.o $(BUILD)/scorer_image.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -Xlinker --exclude-libs,ALL
+
+# A/B builds for measurements (tools/gpu_*.sh): `make variant V=name DEFS="-DSTT_X=1"` -> build/libstt_b200_name.so,
+# selected at load time with STT_B200_LIB=<path> (stt_b200/api.py).  Never shipped: the product is $(OUT).
+variant: $(BUILD)/capi.o $(BUILD)/model_file.o $(BUILD)/tflite_reader.o $(BUILD)/scorer_image.o
+	$(NVCC) $(NVFLAGS) $(DEFS) -c $(SRC)/engine.cu -o $(BUILD)/engine_$(V).o 2> $(BUILD)/ptxas_engine_$(V).log || (cat $(BUILD)/ptxas_engine_$(V).log; false)
+	$(NVCC) $(ARCH) -shared -o $(BUILD)/libstt_b200_$(V).so $(BUILD)/engine_$(V).o $^ -lcudart -Xlinker --exclude-libs,ALL
 
 oracle:
 	$(MAKE) -C oracle

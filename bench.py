@@ -315,6 +315,7 @@ def main():
     batch.decode(1)
     lm = batch.lm_stats()                      # instrumented on the device: words scored / LM calls in that decode
     phase_cycles = batch.phase_cycles()
+    dsc = batch.decoder_scalars()
     batch.set_instrumented(False)
     Q = lm["words_scored"] / float(B)
     dec_bytes = B * (4.0 * C * T + 2.0 * R * W * T + 32.0 * (order + 1) * Q)
@@ -322,6 +323,10 @@ def main():
                           "unit": "GB/s", "frac": dec_bytes / (stages["decode"] * 1e-3) / 1e9 / hbm_gbs,
                           "ms": stages["decode"], "note": "T-serial scan + gather: latency bound (SURVEY 8d)",
                           "lm_words_per_utt": Q, "lm_calls_per_utt": lm["lm_calls"] / float(B),
+                          "lm_cache_misses_per_utt": dsc[11] / float(B), "steps_with_lm_miss_per_utt": dsc[12] / float(B),
+                          "expanding_steps_per_utt": dsc[15] / float(B), "max_candidates": dsc[9] / float(B),
+                          "phase4a_cycles_per_step": {"with_lm_miss": 16.0 * dsc[13] / max(1, dsc[12]),
+                                                      "without": 16.0 * dsc[14] / max(1, dsc[15] - dsc[12])},
                           "phase_share": (lambda pc: {k: round(v / float(max(1, sum(pc.values()))), 3) for k, v in pc.items()})(phase_cycles)}
     dominant = max(roof_all, key=lambda k: roof_all[k]["ms"])
     roofline = dict(roof_all[dominant])

@@ -181,6 +181,9 @@ STT_EXPORT int STTX_BatchPhaseCycles(STTX_Batch* b, unsigned long long* out8);
 /* instrumentation: LSTM kernel cycles of the last forward (max over CTAs): grid-barrier wait, load+MMA span, epilogue */
 STT_EXPORT int STTX_BatchLstmProfile(STTX_Batch* b, unsigned long long* out3);
 STT_EXPORT int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls);
+/* Sums over the batch of the decoder's 16 per-utterance counters (stt_b200/csrc/decoder.cuh Slot::scalars); the statistics
+   build (STTX_BatchSetInstrumented) fills 7.. with LM calls / cache misses / per-phase cycle splits. */
+STT_EXPORT int STTX_BatchDecoderScalars(STTX_Batch* b, unsigned long long* out16);
 /* test hooks */
 STT_EXPORT int STTX_BatchTimesteps(STTX_Batch* b, unsigned int u);
 STT_EXPORT int STTX_BatchCopyFeatures(STTX_Batch* b, unsigned int u, float* out);  /* [T, n_input] */

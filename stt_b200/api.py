@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.realpath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "libstt_b200.so")
+    # STT_B200_LIB: an A/B build of the same library (Makefile `variant`), for measurements only
+    return os.environ.get("STT_B200_LIB") or os.path.join(_HERE, "libstt_b200.so")
 
 
 class STTError(RuntimeError):
@@ -55,7 +56,7 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchSetInstrumented", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout", "STTX_InspectModel", "STTX_InspectModelTensor", "STTX_StreamArenaCompactions",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchDecoderScalars", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout", "STTX_InspectModel", "STTX_InspectModelTensor", "STTX_StreamArenaCompactions",
 ]
 
 
@@ -136,6 +137,7 @@ def lib():
     L.STTX_BatchPhaseCycles.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchLstmProfile.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchLmStats.argtypes = [vp, POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]
+    L.STTX_BatchDecoderScalars.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchCopyFeatures.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchCopyProbs.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchSetProbs.argtypes = [vp, c_void_p, c_void_p, c_uint, c_uint]
@@ -459,6 +461,11 @@ class Batch(object):
         w, c = ctypes.c_ulonglong(), ctypes.c_ulonglong()
         lib().STTX_BatchLmStats(self._impl, byref(w), byref(c))
         return {"words_scored": w.value, "lm_calls": c.value}
+
+    def decoder_scalars(self):
+        arr = (ctypes.c_ulonglong * 16)()
+        lib().STTX_BatchDecoderScalars(self._impl, arr)
+        return [int(x) for x in arr]
 
     def kernel_launches(self):
         return lib().STTX_BatchKernelLaunches(self._impl)

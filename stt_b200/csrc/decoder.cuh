@@ -249,7 +249,7 @@ constexpr uint32_t kStopUnknown = 0xfffffffdu;  // lm_eval_node: the caller does
 //     (= the node's last_space, which the caller has in shared memory): every load below is independent of the others
 //     and a first evaluation starts the trie descent after ONE round trip.
 __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t node, uint32_t stop_hint, uint32_t* word_out,
-                               uint32_t* n_window_out) {
+                               uint32_t* n_window_out, uint32_t* miss_out = nullptr) {
   const sttscorer::ScorerView& v = p.scorer;
   const int order = (int)v.order;
   // lm_cond is both the cache's valid flag (kLmUnset = not computed) and its payload
@@ -303,6 +303,7 @@ __device__ double lm_eval_node(const Slot& s, const DecodeParams& p, uint32_t no
     return cond0;
   }
   // ---- the word ending at `node`
+  if (miss_out) *miss_out = 1;
   uint32_t wid = nd.lm_wid;
   if (wid == kNone) {
     uint32_t sk = kNone;
@@ -464,6 +465,30 @@ __device__ __forceinline__ uint32_t block_scan(uint32_t cnt, uint32_t* warp_sums
   return off;
 }
 
+// Single-barrier variant: every warp redundantly scans the NT/32 warp totals, so nobody waits for warp 0.  `warp_sums`
+// must not be rewritten before another barrier has passed (callers that scan in a loop alternate two buffers).
+template <int NT>
+__device__ __forceinline__ uint32_t block_scan1(uint32_t cnt, uint32_t* warp_sums /*[NT/32]*/, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  main_sync<NT>();
+  const uint32_t v = (lane < NT / 32) ? warp_sums[lane] : 0u;
+  uint32_t inc2 = v;
+#pragma unroll
+  for (int d = 1; d < NT / 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc2, d);
+    if (lane >= d) inc2 += o;
+  }
+  total = __shfl_sync(0xffffffffu, inc2, NT / 32 - 1);
+  return __shfl_sync(0xffffffffu, inc2 - v, warp) + (incl - cnt);
+}
+
 // Shared-memory image of one live list.
 template <int WC>
 struct LiveList {
@@ -492,7 +517,10 @@ struct StepSmem {
 // kInstr compiles in the per-phase clocks and LM counters (bench statistics).  Two CTAs per SM for beams <= 512 (the
 // register budget follows from that), one for the wide instantiation.
 template <int NT, int WC, int NC, bool kInstr>
-__global__ void __launch_bounds__(NT, (WC <= 512 ? 2 : 1))
+#ifndef STT_DEC_MINBLOCKS   // A/B builds only (Makefile `variant`)
+#define STT_DEC_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(NT, (WC <= 512 ? STT_DEC_MINBLOCKS : 1))
 decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
   static_assert(NT == 512, "phase 6 assumes 16 warps (kCommitRounds * 16 warp counts scanned by one warp)");
   __shared__ Slot s_slot;   // the slot's pointers and capacities are read all over the step loop
@@ -514,11 +542,14 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
   __shared__ uint32_t s_rs[2];
   __shared__ uint32_t s_bm[32];  // 1024-bit filter over the ids of the nodes revived by the current commit
   __shared__ double s_nextp[kMaxClasses];   // next row of probabilities, fetched with cp.async (f32 rows use the first half)   // "a node was revived" flags of the last two commits
-  __shared__ uint32_t s_cnt[kCommitRounds * (NT / 32) + 1];
+  __shared__ __align__(16) uint32_t s_cnt[kCommitRounds * (NT / 32)];
   __shared__ uint32_t s_warp[NT / 32 + 1];
+  __shared__ uint32_t s_scan[2][NT / 32];   // block_scan1 buffers (alternated)
   __shared__ float s_red[NT / 32], s_red2[NT / 32];
   __shared__ uint32_t s_u[8];
   __shared__ unsigned long long s_ph[8];
+  __shared__ uint32_t s_ist[8];   // kInstr: 0 LM cache misses of the current step; totals: 1 misses, 2 steps with a miss,
+                                  // 3 / 4 cycles >> 4 of phase 4a in steps with / without a miss, 5 expanding steps
   __shared__ unsigned long long s_thresh;   // phase 5: smallest selected key of the boundary bin
   extern __shared__ __align__(16) uint8_t s_dyn[];
   StepSmem<WC, NC>& sm = *reinterpret_cast<StepSmem<WC, NC>*>(s_dyn);
@@ -533,7 +564,7 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
   if (tid == 0) {
     s_u[6] = 0;
     s_u[7] = 0;
-    for (int q = 0; q < 8; ++q) s_ph[q] = 0;
+    for (int q = 0; q < 8; ++q) { s_ph[q] = 0; s_ist[q] = 0; }
   }
   uint32_t* const aux_base = (WC <= 512) ? sm.aux : s.aux;
   uint32_t* const aux_ord[2] = {aux_base, aux_base + WC};
@@ -572,12 +603,13 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
   };
   // thread c < C waits for ITS element of the prefetched row and turns it into the class log-prob; the blank's thread
   // also prepares the gate (:125) and log(blank) for min_cutoff (:143)
+  const int rcls = NT - 1 - tid;   // class handled by this thread when a row of probabilities is prepared
   auto next_row_ready = [&](int buf) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    const double pd = use64 ? s_nextp[tid] : (double)reinterpret_cast<const float*>(s_nextp)[tid];
-    const float pf = use64 ? (float)s_nextp[tid] : reinterpret_cast<const float*>(s_nextp)[tid];
-    s_logp2[buf][tid] = sttmath::glibc_logf(pf + kFltMin);
-    if (tid == blank) {
+    const double pd = use64 ? s_nextp[rcls] : (double)reinterpret_cast<const float*>(s_nextp)[rcls];
+    const float pf = use64 ? (float)s_nextp[rcls] : reinterpret_cast<const float*>(s_nextp)[rcls];
+    s_logp2[buf][rcls] = sttmath::glibc_logf(pf + kFltMin);
+    if (rcls == blank) {
       s_gate[buf] = pd < 0.999 ? 1u : 0u;
       s_logblank[buf] = log(pd);
     }
@@ -617,16 +649,17 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
     static_assert(kSelBins == 4 * NT, "one uint4 of histogram bins per prefix thread");
     static_assert(sizeof(LiveList<WC>) >= kSelBins * 4 + kSelBoundaryCap * 8, "select scratch must fit in a live list");
     reinterpret_cast<uint4*>(sel_hist)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) s_u[1] = 0;   // length of phase 5's boundary list
     const bool have_next = (step + 1 < in.n_steps);
-    if (have_next && tid < C) {
+    if (have_next && rcls < C) {
       // asynchronous copy straight into shared memory: a register destination would be spilled, and the spill store
       // would wait out the DRAM latency right here
       if (use64) {
-        const double* src = in.probs64 + (size_t)(step + 1) * C + tid;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_nextp[tid])), "l"(src) : "memory");
+        const double* src = in.probs64 + (size_t)(step + 1) * C + rcls;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_nextp[rcls])), "l"(src) : "memory");
       } else {
-        const float* src = in.probs + (size_t)(step + 1) * C + tid;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(reinterpret_cast<float*>(s_nextp) + tid)), "l"(src) : "memory");
+        const float* src = in.probs + (size_t)(step + 1) * C + rcls;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(reinterpret_cast<float*>(s_nextp) + rcls)), "l"(src) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -670,7 +703,7 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
     main_sync<NT>();
     PHASE_MARK(1);
     if (!start_expanding || overflow) {
-      if (have_next && tid < C) next_row_ready(cb ^ 1);
+      if (have_next && rcls < C) next_row_ready(cb ^ 1);
       main_sync<NT>();
       continue;
     }
@@ -707,13 +740,15 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
                 !(full_beam && s_logp[p.space_id] + si < min_cutoff)) {
               uint32_t wid, nw;
               // (float)(cond * alpha): ctc_beam_search_decoder.cpp:239
-              double cond = lm_eval_node(s, p, L.node[i], L.lsp[i], &wid, &nw);
+              uint32_t miss = 0;
+              double cond = lm_eval_node(s, p, L.node[i], L.lsp[i], &wid, &nw, kInstr ? &miss : nullptr);
               if (p.n_hot > 0) cond += (double)hot_word_boost(s, p, L.node[i], wid);
               sm.lmterm[i] = (float)(cond * sv.alpha);
               sm.lmwid[i] = wid;
               if (kInstr) {
                 atomicAdd(&s_u[6], nw);
                 atomicAdd(&s_u[7], 1u);
+                if (miss) atomicAdd(&s_ist[0], 1u);
               }
             }
             allow = L.mask[i] & all_labels & ~sm.child[i];
@@ -728,7 +763,7 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
           }
         }
         uint32_t total;
-        const uint32_t off = run_base + block_scan<NT, (WC > NT)>(__popc(allow), s_warp, total);
+        const uint32_t off = run_base + block_scan1<NT>(__popc(allow), s_scan[(base / NT) & 1], total);
         if (i < n_live) {
           sm.child[i] = allow;   // the live-child masks are no longer needed (phase 3 uses plive)
           sm.lmq[i] = off;       // reuse: offset of this prefix's first child among the new candidates
@@ -736,6 +771,15 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
         run_base += total;
       }
       n_new = run_base;
+    }
+    if (kInstr && tid == 0) {   // the scan's barriers have passed: every LM evaluation of this step is done
+      const long long t4a = clock64();
+      const uint32_t m = s_ist[0];
+      s_ist[0] = 0;
+      s_ist[1] += m;
+      s_ist[2] += m ? 1u : 0u;
+      s_ist[m ? 3 : 4] += (uint32_t)((unsigned long long)(t4a - ph_t0) >> 4);
+      s_ist[5] += 1u;
     }
     const uint32_t N = n_live + n_new;
     if (N > s.cand_cap) { overflow = 1; main_sync<NT>(); continue; }
@@ -870,7 +914,7 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
     }
     main_sync<NT>();
     for (uint32_t i = tid; i < (uint32_t)WC; i += NT) sm.child[i] = 0;  // ready for the next step's phase 0
-    if (have_next && tid < C) next_row_ready(cb ^ 1);
+    if (have_next && rcls < C) next_row_ready(cb ^ 1);
     PHASE_MARK(4);
 
     // ---- phase 5: exact top-W selection on the 64-bit key (:263-274 nth_element + prefix_compare).
@@ -914,28 +958,51 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
       }
       if (lane == 0) s_warp[warp] = suffix;
       main_sync<NT>();
-      uint32_t above_warps = 0;
+      // every warp locates the boundary bin by itself: which warp's 128 bins the W-th best key falls in (from the 16 warp
+      // totals), then a second look at that warp's bins -- no broadcast through shared memory, no further barrier
+      uint32_t k_rem, cnt;
+      {
+        const uint32_t wv = (lane < NT / 32) ? s_warp[lane] : 0u;
+        uint32_t wsuf = wv;   // inclusive over warps >= lane
 #pragma unroll
-      for (int w = 1; w < NT / 32; ++w) above_warps += (w > warp) ? s_warp[w] : 0u;
-      const uint32_t incl = above_warps + suffix, above = incl - mine;
-      if (above < (uint32_t)W && incl >= (uint32_t)W) {
-        const uint32_t hq[4] = {hv.x, hv.y, hv.z, hv.w};
-        uint32_t cum = above;
-#pragma unroll
-        for (int q = 3; q >= 0; --q) {
-          if (cum + hq[q] >= (uint32_t)W) {
-            s_u[2] = (uint32_t)(tid * 4 + q);
-            s_u[3] = (uint32_t)W - cum;   // still needed from this bin
-            s_u[4] = hq[q];               // elements in this bin
-            s_u[1] = 0;                   // boundary list length
-            break;
-          }
-          cum += hq[q];
+        for (int d = 1; d < NT / 32; d <<= 1) {
+          const uint32_t o = __shfl_down_sync(0xffffffffu, wsuf, d);
+          if (lane + d < NT / 32) wsuf += o;
         }
+        const uint32_t hit = __ballot_sync(0xffffffffu, lane < NT / 32 && wsuf - wv < (uint32_t)W && wsuf >= (uint32_t)W);
+        const int bw = __ffs(hit) - 1;                               // exactly one warp qualifies (N > W)
+        const uint32_t above_bw = __shfl_sync(0xffffffffu, wsuf - wv, bw);
+        const uint4 h2 = reinterpret_cast<const uint4*>(sel_hist)[bw * 32 + lane];
+        const uint32_t m2 = h2.x + h2.y + h2.z + h2.w;
+        uint32_t suf2 = m2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_down_sync(0xffffffffu, suf2, d);
+          if (lane + d < 32) suf2 += o;
+        }
+        const uint32_t incl2 = above_bw + suf2, above2 = incl2 - m2;
+        const uint32_t hit2 = __ballot_sync(0xffffffffu, above2 < (uint32_t)W && incl2 >= (uint32_t)W);
+        const int bl = __ffs(hit2) - 1;
+        uint32_t fb = 0, fk = 0, fc = 0;
+        {
+          const uint32_t hq[4] = {h2.x, h2.y, h2.z, h2.w};
+          uint32_t cum = above2;
+          bool found = false;
+#pragma unroll
+          for (int q = 3; q >= 0; --q) {
+            if (!found && cum + hq[q] >= (uint32_t)W) {
+              fb = (uint32_t)((bw * 32 + lane) * 4 + q);
+              fk = (uint32_t)W - cum;   // still needed from this bin
+              fc = hq[q];               // elements in this bin
+              found = true;
+            }
+            cum += hq[q];
+          }
+        }
+        sel_bin = __shfl_sync(0xffffffffu, fb, bl);
+        k_rem = __shfl_sync(0xffffffffu, fk, bl);
+        cnt = __shfl_sync(0xffffffffu, fc, bl);
       }
-      main_sync<NT>();
-      sel_bin = s_u[2];
-      const uint32_t k_rem = s_u[3], cnt = s_u[4];
       if (cnt == k_rem) {
         sel_mode = 1;            // the whole boundary bin is selected
         need_radix = false;
@@ -1037,29 +1104,31 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
         if (lane == 0) s_cnt[q * (NT / 32) + warp] = __popc(bal[q]);
       }
       main_sync<NT>();
-      if (warp == 0) {
+      uint32_t round_off[kCommitRounds], round_total;
+      {
+        // entry (q, w) sits at index q * 16 + w; lane l holds entries 4l .. 4l+3, i.e. round l / 4, warps 4 (l % 4) .. +3
         constexpr int PER = kCommitRounds * (NT / 32) / 32;  // entries per lane
-        uint32_t v[PER], sum = 0;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) { v[i] = s_cnt[lane * PER + i]; sum += v[i]; }
+        static_assert(PER == 4, "lane <-> (round, warp) mapping below");
+        const uint4 v4 = reinterpret_cast<const uint4*>(s_cnt)[lane];
+        const uint32_t sum = v4.x + v4.y + v4.z + v4.w;
         uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += o;
         }
-        uint32_t run = incl - sum;
+        const int sub = warp & 3;
+        const uint32_t pre = (incl - sum) + (sub > 0 ? v4.x : 0u) + (sub > 1 ? v4.y : 0u) + (sub > 2 ? v4.z : 0u);
 #pragma unroll
-        for (int i = 0; i < PER; ++i) { s_cnt[lane * PER + i] = run; run += v[i]; }
-        if (lane == 31) s_cnt[kCommitRounds * (NT / 32)] = incl;
+        for (int q = 0; q < kCommitRounds; ++q) round_off[q] = __shfl_sync(0xffffffffu, pre, q * 4 + (warp >> 2));
+        round_total = __shfl_sync(0xffffffffu, incl, 31);
       }
-      main_sync<NT>();
 #pragma unroll
       for (int q = 0; q < kCommitRounds; ++q) {
         const uint32_t e = g0 + (uint32_t)q * NT + tid;
         if (e >= N) break;
         const bool keep = (bal[q] >> lane) & 1u;
-        const uint32_t pos = out_base + s_cnt[q * (NT / 32) + warp] + __popc(bal[q] & ((1u << lane) - 1u));
+        const uint32_t pos = out_base + round_off[q] + __popc(bal[q] & ((1u << lane) - 1u));
         const unsigned long long key = K[e];
         if (e < n_live) {
           const uint32_t nd = L.node[e];
@@ -1101,7 +1170,7 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
           asm volatile("prefetch.global.L2 [%0];" ::"l"(s.ht + (ht_hash(hw >> 24) & s.ht_mask)));
         }
       }
-      out_base += s_cnt[kCommitRounds * (NT / 32)];
+      out_base += round_total;
       main_sync<NT>();
     }
     PHASE_MARK(7);
@@ -1254,8 +1323,10 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
     }
     if (max_cand > s.scalars[9]) s.scalars[9] = max_cand;
     s.scalars[10] += spills;
-    if (kInstr)
+    if (kInstr) {
       for (int q = 0; q < 8; ++q) s.phase_cycles[q] += s_ph[q];
+      for (int q = 1; q <= 5; ++q) s.scalars[10 + q] += s_ist[q];
+    }
   }
 }
 

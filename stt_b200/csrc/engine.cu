@@ -1430,6 +1430,17 @@ int batch_lm_stats(Batch* b, unsigned long long* words, unsigned long long* call
   return 0;
 }
 
+int batch_decoder_scalars(Batch* b, unsigned long long* out16) {
+  cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
+  for (int q = 0; q < 16; ++q) out16[q] = 0;
+  for (int u = 0; u < b->B; ++u) {
+    uint32_t sc[16];
+    CUDA_OK(cudaMemcpy(sc, b->h_slots[u].scalars, sizeof(sc), cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 16; ++q) out16[q] += sc[q];
+  }
+  return 0;
+}
+
 int batch_copy_features(Batch* b, int utt, float* out) {
   cudaSetDevice(b->e->device);  // CUDA's current device is per host thread
   if (utt < 0 || utt >= b->B) return -1;

@@ -52,6 +52,7 @@ void batch_set_instrumented(Batch* b, bool on);              // decoder statisti
 int batch_phase_cycles(Batch* b, unsigned long long* out8);  // instrumentation: summed over utterances
 int batch_lstm_profile(Batch* b, unsigned long long* out3);  // max over CTAs: barrier-wait, load+MMA span, epilogue cycles
 int batch_lm_stats(Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls);  // instrumentation
+int batch_decoder_scalars(Batch* b, unsigned long long* out16);   // sums over the batch of Slot::scalars (decoder.cuh)
 int batch_T(const Batch* b, int utt);                        // timesteps of utterance `utt` after upload
 int batch_copy_features(Batch* b, int utt, float* out);      // [T, n_input] fp32 MFCC
 int batch_copy_probs(Batch* b, int utt, float* out);         // [T, n_classes]
