@@ -325,6 +325,7 @@ def main():
                           "lm_words_per_utt": Q, "lm_calls_per_utt": lm["lm_calls"] / float(B),
                           "lm_cache_misses_per_utt": dsc[11] / float(B), "steps_with_lm_miss_per_utt": dsc[12] / float(B),
                           "expanding_steps_per_utt": dsc[15] / float(B), "max_candidates": dsc[9] / float(B),
+                          "steps_with_candidates_in_global_memory_per_utt": dsc[10] / float(B),
                           "phase4a_cycles_per_step": {"with_lm_miss": 16.0 * dsc[13] / max(1, dsc[12]),
                                                       "without": 16.0 * dsc[14] / max(1, dsc[15] - dsc[12])},
                           "phase_share": (lambda pc: {k: round(v / float(max(1, sum(pc.values()))), 3) for k, v in pc.items()})(phase_cycles)}

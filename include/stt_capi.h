@@ -184,6 +184,11 @@ STT_EXPORT int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored
 /* Sums over the batch of the decoder's 16 per-utterance counters (stt_b200/csrc/decoder.cuh Slot::scalars); the statistics
    build (STTX_BatchSetInstrumented) fills 7.. with LM calls / cache misses / per-phase cycle splits. */
 STT_EXPORT int STTX_BatchDecoderScalars(STTX_Batch* b, unsigned long long* out16);
+/* Vocabulary pruning of the batch's following decodes = DecoderState::init's cutoff_prob / cutoff_top_n
+   (native_client/ctcdecode/ctc_beam_search_decoder.cpp:22-61, get_pruned_emissions :328-358).  The reference's C API fixes
+   them at 1.0 / 40 (native_client/stt.cc:539-540), which is the default here; its decoder-only Python package
+   (native_client/ctcdecode/__init__.py:122-178) passes the caller's values. */
+STT_EXPORT int STTX_BatchSetCutoff(STTX_Batch* b, double cutoff_prob, unsigned int cutoff_top_n);
 /* test hooks */
 STT_EXPORT int STTX_BatchTimesteps(STTX_Batch* b, unsigned int u);
 STT_EXPORT int STTX_BatchCopyFeatures(STTX_Batch* b, unsigned int u, float* out);  /* [T, n_input] */

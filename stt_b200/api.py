@@ -56,7 +56,7 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchSetInstrumented", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchDecoderScalars", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout", "STTX_InspectModel", "STTX_InspectModelTensor", "STTX_StreamArenaCompactions",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchDecoderScalars", "STTX_BatchSetCutoff", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout", "STTX_InspectModel", "STTX_InspectModelTensor", "STTX_StreamArenaCompactions",
 ]
 
 
@@ -138,6 +138,7 @@ def lib():
     L.STTX_BatchLstmProfile.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchLmStats.argtypes = [vp, POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong)]
     L.STTX_BatchDecoderScalars.argtypes = [vp, POINTER(ctypes.c_ulonglong)]
+    L.STTX_BatchSetCutoff.argtypes = [vp, ctypes.c_double, c_uint]
     L.STTX_BatchCopyFeatures.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchCopyProbs.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchSetProbs.argtypes = [vp, c_void_p, c_void_p, c_uint, c_uint]
@@ -461,6 +462,10 @@ class Batch(object):
         w, c = ctypes.c_ulonglong(), ctypes.c_ulonglong()
         lib().STTX_BatchLmStats(self._impl, byref(w), byref(c))
         return {"words_scored": w.value, "lm_calls": c.value}
+
+    def set_cutoff(self, cutoff_prob=1.0, cutoff_top_n=40):
+        """Vocabulary pruning of the following decodes (the decoder-only surface's cutoff_prob / cutoff_top_n)."""
+        self._ok(lib().STTX_BatchSetCutoff(self._impl, float(cutoff_prob), int(cutoff_top_n)), "BatchSetCutoff")
 
     def decoder_scalars(self):
         arr = (ctypes.c_ulonglong * 16)()

@@ -608,6 +608,9 @@ int STTX_BatchLstmProfile(STTX_Batch* b, unsigned long long* out3) {
 int STTX_BatchLmStats(STTX_Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls) {
   return stteng::batch_lm_stats(b->dev, words_scored, lm_calls) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
 }
+int STTX_BatchSetCutoff(STTX_Batch* b, double cutoff_prob, unsigned int cutoff_top_n) {
+  return stteng::batch_set_cutoff(b->dev, cutoff_prob, (int)cutoff_top_n) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
+}
 int STTX_BatchDecoderScalars(STTX_Batch* b, unsigned long long* out16) {
   return stteng::batch_decoder_scalars(b->dev, out16) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
 }

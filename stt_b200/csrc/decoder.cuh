@@ -189,6 +189,10 @@ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t chr
   return ((unsigned long long)sortable(score) << 32) | ((unsigned long long)(255u - (chr & 0xffu)) << 24) |
          (unsigned long long)(0xffffffu - (idx & 0xffffffu));
 }
+// Tie-break field of a NEW candidate's key: candidates are laid out live prefixes first, then new children ordered by
+// (parent's live index, label), so 0x1000 + parent * 32 + label grows with the candidate's position -- the same total
+// order as the position itself -- and lets the commit phase recover (parent, label) from the key alone.
+__device__ __forceinline__ uint32_t new_cand_idx(uint32_t parent_live, uint32_t label) { return 0x1000u + parent_live * 32u + label; }
 // order in which the reference's sorted loop visits two live prefixes: true if x comes before y
 __device__ __forceinline__ bool visits_before(float sx, uint32_t cx, uint32_t ix, float sy, uint32_t cy, uint32_t iy) {
   if (sx != sy) return sx > sy;
@@ -404,6 +408,111 @@ __device__ float hot_word_boost(const Slot& s, const DecodeParams& p, uint32_t n
   return boost;
 }
 
+// ------------------------------------------------------------------------------------------------ UTF-8 mode helpers
+// (bytes-output scorers; used by the general kernel of decoder_general.cuh and by the finalize kernel below)
+// A node of a UTF-8 decode keeps, in the two words the word mode uses for its space bookkeeping:
+//   Node::last_space  the CONTEXT node of the code point this byte belongs to = the parent of that code point's lead
+//                     byte (the node where the previous code point ended, or the root)
+//   Node::ord         distance_to_codepoint_boundary (bytes since the lead byte, inclusive) | lead byte << 8
+__device__ __forceinline__ int utf8_needed_bytes(uint32_t lead) {   // scorer.cpp:280-292
+  if ((lead >> 3) == 0x1Eu) return 4;
+  if ((lead >> 4) == 0x0Eu) return 3;
+  if ((lead >> 5) == 0x06u) return 2;
+  if ((lead >> 7) == 0x00u) return 1;
+  return 0;   // invalid lead byte: never a boundary
+}
+__device__ __forceinline__ bool utf8_is_lead(uint32_t byte) { return (byte & 0xC0u) != 0x80u; }   // byte_is_codepoint_boundary
+__device__ __forceinline__ bool utf8_completes(uint32_t ord) { return utf8_needed_bytes((ord >> 8) & 0xffu) == (int)(ord & 0xffu); }
+// cp fields of the child (parent record, label)
+__device__ __forceinline__ void utf8_child_fields(const sttscorer::ScorerView& v, const Node& par, uint32_t par_id, uint32_t c,
+                                                  uint32_t* ord_out, uint32_t* ctx_out) {
+  const uint32_t byte = v.label_bytes[c][0];
+  if (utf8_is_lead(byte) || par.chr == kRootChar) {
+    *ord_out = 1u | (byte << 8);
+    *ctx_out = par_id;
+  } else {
+    *ord_out = (((par.ord & 0xffu) + 1u) & 0xffu) | (par.ord & 0xff00u);
+    *ctx_out = par.last_space;
+  }
+}
+
+// Vocabulary id of the bytes of the (possibly incomplete) code point that ends at `node`, optionally followed by the
+// bytes of one more label `extra` (a candidate child that does not exist yet; kNone = none).
+__device__ uint32_t utf8_unit_id(const Slot& s, const sttscorer::ScorerView& v, uint32_t node, uint32_t n_back, uint32_t extra) {
+  uint8_t buf[40];
+  int len = 0;
+  if (extra != kNone)
+    for (int q = (int)v.label_len[extra] - 1; q >= 0; --q) buf[len++] = v.label_bytes[extra][q];
+  uint32_t w = node;
+  for (uint32_t k = 0; k < n_back && w != kNone && len <= 32; ++k) {
+    const Node nd = s.nodes[w];
+    if (nd.chr == kRootChar) break;
+    for (int q = (int)v.label_len[nd.chr] - 1; q >= 0; --q) buf[len++] = v.label_bytes[nd.chr][q];
+    w = nd.parent;
+  }
+  for (int a = 0, b = len - 1; a < b; ++a, --b) { const uint8_t t = buf[a]; buf[a] = buf[b]; buf[b] = t; }
+  return sttscorer::vocab_index(v, buf, (uint32_t)len);
+}
+
+// Scorer::make_ngram + get_log_cond_prob in UTF-8 mode, literally: the <= order code points that end at the prefix
+// (`node` followed by the optional candidate label `extra`), scored from BeginSentence when the window holds fewer
+// than `order` units, from the null context otherwise; OOV_SCORE if a unit is not in the vocabulary.  Also returns the
+// hot-word boost of the window (ctc_beam_search_decoder.cpp:224-236).  A unit's id is cached in Node::lm_wid of the
+// node that ends it.
+__device__ double utf8_window_cond(const Slot& s, const DecodeParams& p, uint32_t node, uint32_t extra, float* boost_out) {
+  const sttscorer::ScorerView& v = p.scorer;
+  const int order = (int)v.order;
+  uint32_t ids_rev[sttscorer::kMaxOrder];
+  int n = 0;
+  uint32_t cur = node;
+  if (extra != kNone) {
+    // the unit that the candidate label completes (or leaves incomplete)
+    const Node nd = s.nodes[node];
+    uint32_t ord, ctx;
+    utf8_child_fields(v, nd, node, extra, &ord, &ctx);
+    ids_rev[n++] = utf8_unit_id(s, v, node, (ord & 0xffu) - 1u, extra);
+    cur = ctx;
+  }
+  while (n < order && cur != kNone) {
+    const Node nd = s.nodes[cur];
+    if (nd.chr == kRootChar) break;
+    uint32_t id = nd.lm_wid;
+    if (id == kNone || !utf8_completes(nd.ord)) {
+      id = utf8_unit_id(s, v, cur, nd.ord & 0xffu, kNone);
+      if (utf8_completes(nd.ord)) s.nodes[cur].lm_wid = id;   // every writer writes the same value
+    }
+    ids_rev[n++] = id;
+    cur = nd.last_space;
+  }
+  uint32_t ids[sttscorer::kMaxOrder];
+  float boost = 0.0f;
+  for (int i = 0; i < n; ++i) {
+    ids[i] = ids_rev[n - 1 - i];
+    if (p.n_hot > 0 && ids[i] != 0) {
+      bool hit = false;
+      float b = 0.0f;
+      for (int h = 0; h < p.n_hot; ++h)
+        if (p.hot_id[h] == ids[i]) { b = p.hot_boost[h]; hit = true; }
+      if (hit) boost += b;
+    }
+  }
+  if (boost_out) *boost_out = boost;
+  if (n == 0) return 0.0;   // get_log_cond_prob of no words (scorer.cpp:325,343)
+  return sttscorer::log_cond_prob_ids(v, ids, n, n < order);
+}
+
+// LM term (before alpha) of an EXISTING node whose last byte completes a code point; cached in Slot::lm_cond.
+__device__ double utf8_node_cond(const Slot& s, const DecodeParams& p, uint32_t node) {
+  if (p.n_hot == 0) {
+    const unsigned long long bits = reinterpret_cast<const unsigned long long*>(s.lm_cond)[node];
+    if (bits != kLmUnset) return __longlong_as_double((long long)bits);
+  }
+  float boost = 0.0f;
+  const double cond = utf8_window_cond(s, p, node, kNone, &boost);
+  if (p.n_hot == 0) s.lm_cond[node] = cond;
+  return cond + (double)boost;
+}
+
 // ------------------------------------------------------------------------------------------------ init
 // DecoderState::init (:22-61): root prefix with score = log_prob_b_prev = 0.
 __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start, uint32_t ht_gen) {
@@ -510,8 +619,11 @@ struct StepSmem {
   // word ordinal + created-children mask of each live prefix, double buffered: [ord0 | ord1 | cmask0 | cmask1].  The
   // wide-beam instantiation (WC > 512, one CTA per SM) has no room left and keeps them in Slot::aux (global memory).
   uint32_t aux[WC <= 512 ? 4 * WC : 1];
+  // per-step candidates: a 64-bit key each.  Only the live prefixes' entries carry payload (their updated blank / non-blank
+  // log-probs, p0 / p1); a NEW candidate's parent and label are part of its key (new_cand_idx), so 8 bytes per candidate
+  // buy room for 5632 candidates where 16 bytes bought 3072, and steps that spill to global memory become rare.
   unsigned long long key[NC > 0 ? NC : 1];
-  uint32_t p0[NC > 0 ? NC : 1], p1[NC > 0 ? NC : 1];
+  uint32_t p0[NC > 0 ? WC : 1], p1[NC > 0 ? WC : 1];
 };
 
 // kInstr compiles in the per-phase clocks and LM counters (bench statistics).  Two CTAs per SM for beams <= 512 (the
@@ -787,8 +899,8 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
     const bool in_smem = (NC > 0) && (N <= (uint32_t)NC);
     if (!in_smem) ++spills;
     unsigned long long* const K = in_smem ? sm.key : s.c_key;
-    uint32_t* const P0 = in_smem ? sm.p0 : s.c_p0;
-    uint32_t* const P1 = in_smem ? sm.p1 : s.c_p1;
+    uint32_t* const P0 = (NC > 0) ? sm.p0 : s.c_p0;   // live entries only (j < n_live <= WC)
+    uint32_t* const P1 = (NC > 0) ? sm.p1 : s.c_p1;
 
     // ---- phase 3: updated values of the live prefixes (blank / repeat / pulled extension), :150-256
     float cand_min = 3.402823466e+38f, cand_max = kNegMax;   // over this thread's finite candidate scores (phase 5 bins)
@@ -879,8 +991,7 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
           lp = (float)((double)lp + sv.beta);
         }
         if (lp > kNegMax) { cand_min = fminf(cand_min, lp); cand_max = fmaxf(cand_max, lp); }
-        K[e] = make_key(lp, (uint32_t)c, e);
-        P0[e] = ii | ((uint32_t)c << 16);   // the child's dictionary state is looked up in phase 6, for survivors only
+        K[e] = make_key(lp, (uint32_t)c, new_cand_idx(ii, (uint32_t)c));   // the child's dictionary state is looked up in phase 6, for survivors only
       };
       const bool heavy = __popc(allow) > 6;
       uint32_t hv = __ballot_sync(0xffffffffu, heavy);
@@ -1163,7 +1274,8 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
           Nx.score[pos] = lp;
           Nx.b[pos] = kNegMax;
           Nx.nb[pos] = lp;
-          const uint32_t pk = P0[e];
+          const uint32_t kc = 255u - ((uint32_t)(key >> 24) & 0xffu);
+          const uint32_t pk = ((0xffffffu - ((uint32_t)key & 0xffffffu) - 0x1000u) >> 5) | (kc << 16);
           sm.lmq[pos] = pk;  // parent live index | label << 16
           // the (parent,label) hash slot is a DRAM miss: start it now, (ii) touches it after the barrier
           const unsigned long long hw = ht_pack(s.ht_gen, L.node[pk & 0xffffu], (pk >> 16) & 0xffu, 0u);
@@ -1356,7 +1468,16 @@ __global__ void __launch_bounds__(NT) decoder_finalize_kernel(Slot* slots, const
     const uint32_t nd = s.node[i];
     float sc = s.score[i];
     const uint32_t c = s.nodes[nd].chr;
-    if (p.has_scorer && i < (uint32_t)p.beam && c != kRootChar && (int)c != p.space_id) {
+    if (p.has_scorer && p.scorer.is_utf8) {
+      // UTF-8 mode (:291-300): prefix_boundary is the prefix itself, so the root is scored too (an empty n-gram: 0), and so
+      // is every prefix whose last byte leaves a code point unfinished (its window ends with that partial unit)
+      if (i < (uint32_t)p.beam && (c == kRootChar || !utf8_completes(s.nodes[nd].ord))) {
+        const double cond = (c == kRootChar) ? 0.0 : utf8_window_cond(s, p, nd, kNone, nullptr);
+        float add = (float)(cond * p.scorer.alpha);
+        add = (float)((double)add + p.scorer.beta);
+        sc = sc + add;
+      }
+    } else if (p.has_scorer && i < (uint32_t)p.beam && c != kRootChar && (int)c != p.space_id) {
       uint32_t wid_unused, nw_unused;
       float add = (float)(lm_eval_node(s, p, nd, kStopUnknown, &wid_unused, &nw_unused) * p.scorer.alpha);
       add = (float)((double)add + p.scorer.beta);

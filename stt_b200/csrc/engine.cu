@@ -18,6 +18,7 @@
 #include <thread>
 
 #include "decoder.cuh"
+#include "decoder_general.cuh"
 #include "gemm_tc.cuh"
 #include "lstm2_tc.cuh"
 #include "probe_tc.cuh"
@@ -110,7 +111,7 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
 // Kernel attributes (opt-in shared memory) are per DEVICE: each Engine remembers which of its kernels it has configured
 // on its device in a bit mask.  Setting an attribute twice is harmless, so concurrent host threads need no lock.
 enum KernelBit {
-  kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
+  kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitGemmSoftmaxWide, kBitDecGeneral, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
   kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitDec512, kBitDec512I, kBitDec2048, kBitDec2048I
 };
 template <class K>
@@ -130,7 +131,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::Gem
   constexpr int bit = (AMODE == sttgemm::kWindows3D) ? kBitGemmWin
                       : (EPI == sttgemm::kEpiClipReluF16) ? kBitGemmRelu
                       : (EPI == sttgemm::kEpiBiasF32)     ? kBitGemmBias
-                                                          : kBitGemmSoftmax;
+                      : (BN == 32)                        ? kBitGemmSoftmax
+                                                          : kBitGemmSoftmaxWide;
   if (ensure_smem(cfg_mask, bit, kern, L::kTotal)) return -1;
   int n_tiles_m;
   if (AMODE == sttgemm::kWindows3D)
@@ -161,10 +163,12 @@ struct DeviceScorer {
   int4* fst_arc4 = nullptr;            // per arc {child dictionary state, its first arc, its label mask, word-ordinal skip} x2
   uint32_t* fst_space_skip = nullptr;  // word-ordinal tables (decoder.cuh DecodeParams), null when not applicable
   uint32_t* ord2wid = nullptr;
+  uint2* gstate = nullptr;             // general kernel (decoder_general.cuh): per state {first arc, number of arcs}
+  int2* garc = nullptr;                //                                        per arc {label, child dictionary state}
   std::vector<uint8_t> vocab_host;     // the vocabulary-hash section, kept on the host for hot-word id lookups
   ~DeviceScorer() {
     cudaSetDevice(device);
-    for (void* p : {(void*)blob, (void*)fst_state2, (void*)fst_arc4, (void*)fst_space_skip, (void*)ord2wid})
+    for (void* p : {(void*)blob, (void*)fst_state2, (void*)fst_arc4, (void*)fst_space_skip, (void*)ord2wid, (void*)gstate, (void*)garc})
       if (p) cudaFree(p);
   }
 };
@@ -174,6 +178,7 @@ struct Engine {
   sttmodel::HostModel hm;
   int device = 0, num_sms = 0;
   int Hp = 0, Cp = 0, K1 = 0;  // padded hidden / cell dims, layer-1 K (= (2c+1)*32)
+  int N6 = 32;                 // padded class count of the output layer: 32, or 256 for alphabets beyond 31 labels
   // weights: [N, K] fp16 K-major
   __half *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wx = nullptr, *wh = nullptr, *w5 = nullptr, *w6 = nullptr;
   float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *bx = nullptr, *b5 = nullptr, *b6 = nullptr;
@@ -311,7 +316,8 @@ int build_weights(Engine* e) {
   };
   std::vector<__half> w2 = to_nk_f16(m.w2.data(), H, H, Hp, Hp), w3 = to_nk_f16(m.w3.data(), H, H, Hp, Hp);
   std::vector<__half> w5 = to_nk_f16(m.w5.data(), C, H, Cp, Hp);
-  std::vector<__half> w6 = to_nk_f16(m.w6.data(), H, K, Hp, 32);
+  e->N6 = (K <= 32) ? 32 : 256;
+  std::vector<__half> w6 = to_nk_f16(m.w6.data(), H, K, Hp, e->N6);
   // LSTM kernel [H + C, 4C], gate blocks i|j|f|o (rnn_cell_impl.py:1060-1061) -> gate-interleaved rows cell*4 + g
   std::vector<__half> wx((size_t)4 * Cp * Hp, __float2half_rn(0.f)), wh((size_t)4 * Cp * Cp, __float2half_rn(0.f));
   std::vector<float> bx((size_t)4 * Cp, 0.f);
@@ -327,14 +333,14 @@ int build_weights(Engine* e) {
       upload(&e->w5, w5) || upload(&e->w6, w6))
     return -1;
   std::vector<float> b1 = pad_bias(m.b1, Hp), b2 = pad_bias(m.b2, Hp), b3 = pad_bias(m.b3, Hp), b5 = pad_bias(m.b5, Hp),
-                     b6 = pad_bias(m.b6, 32);
+                     b6 = pad_bias(m.b6, e->N6);
   if (upload(&e->b1, b1) || upload(&e->b2, b2) || upload(&e->b3, b3) || upload(&e->bx, bx) || upload(&e->b5, b5) ||
       upload(&e->b6, b6))
     return -1;
   bool ok = make_tmap_2d(&e->tm_w1, e->w1, Hp, K1p, K1p, 256) && make_tmap_2d(&e->tm_w2, e->w2, Hp, Hp, Hp, 256) &&
             make_tmap_2d(&e->tm_w3, e->w3, Hp, Hp, Hp, 256) && make_tmap_2d(&e->tm_wx, e->wx, 4 * Cp, Hp, Hp, 256) &&
             make_tmap_2d(&e->tm_wh, e->wh, 4 * Cp, Cp, Cp, 64) && make_tmap_2d(&e->tm_w5, e->w5, Hp, Cp, Cp, 256) &&
-            make_tmap_2d(&e->tm_w6, e->w6, 32, Hp, Hp, 32);
+            make_tmap_2d(&e->tm_w6, e->w6, e->N6, Hp, Hp, e->N6);
   return ok ? 0 : -1;
 }
 
@@ -371,8 +377,8 @@ Engine* engine_create(const sttmodel::HostModel& m, std::string* err) {
     delete e;
     return nullptr;
   }
-  if (m.n_classes > 33 || m.n_classes < 2) {
-    if (err) *err = "alphabets larger than 32 labels are not supported yet";
+  if (m.n_classes > 256 || m.n_classes < 2) {
+    if (err) *err = "alphabets larger than 255 labels are not supported";
     delete e;
     return nullptr;
   }
@@ -523,7 +529,6 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
   sttscorer::ScorerView v;
   int err = sttscorer::parse_scorer(bytes, n, ab, &v);
   if (err) return err;
-  if (v.is_utf8) return sttscorer::SCORER_INVALID_TRIE;  // bytes-output mode: SURVEY 8(f) rank 4, not built yet
   // Everything is parsed, validated and uploaded into a NEW object; the engine's current scorer is replaced only when
   // all of it has succeeded (a failed STT_EnableExternalScorer leaves the old scorer enabled, stt.cc:428-432).
   std::shared_ptr<DeviceScorer> ds = std::make_shared<DeviceScorer>();
@@ -533,7 +538,7 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
   // per state the set of labels with an outgoing arc, per arc the child's dictionary state, i.e. Start() when the
   // arc's target is final ("restart spell checker at the start state"), else the target.
   v.blob = bytes;  // host view for the preprocessing
-  std::vector<uint2> st2((size_t)v.fst_nstates);
+  std::vector<uint2> st2((size_t)v.fst_nstates), gst((size_t)v.fst_nstates);
   std::vector<int2> ar2((size_t)v.fst_narcs);
   for (int64_t q = 0; q < v.fst_nstates; ++q) {
     const uint8_t* srec = bytes + v.fst_states_off + (uint64_t)q * 20;
@@ -558,7 +563,10 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
       ar2[pos + a] = make_int2(il, fin ? (int32_t)v.fst_start : nx);
     }
     st2[(size_t)q] = make_uint2(pos, mask);
+    gst[(size_t)q] = make_uint2(pos, narcs);
   }
+  std::vector<int2> gar(ar2.size());
+  for (size_t i = 0; i < ar2.size(); ++i) gar[i] = make_int2(ar2[i].x - 1, ar2[i].y);   // label = ilabel - 1 (path_trie.cpp:62)
   std::vector<uint32_t> skip, space_skip;
   build_word_ordinals(e, ds.get(), v, bytes, &skip, &space_skip);
   // two 16-byte words per arc: {child state, child's first arc, child's label mask, ordinal skip} and
@@ -571,13 +579,17 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
   }
   if (cudaMalloc(reinterpret_cast<void**>(&ds->blob), n + 16) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&ds->fst_state2), std::max<size_t>(st2.size(), 1) * sizeof(uint2)) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&ds->fst_arc4), std::max<size_t>(ar4.size(), 1) * sizeof(int4)) != cudaSuccess) {
+      cudaMalloc(reinterpret_cast<void**>(&ds->fst_arc4), std::max<size_t>(ar4.size(), 1) * sizeof(int4)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&ds->gstate), std::max<size_t>(gst.size(), 1) * sizeof(uint2)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&ds->garc), std::max<size_t>(gar.size(), 1) * sizeof(int2)) != cudaSuccess) {
     cudaGetLastError();
     return sttscorer::SCORER_UNREADABLE;
   }
   if (cudaMemset(ds->blob + n, 0, 16) != cudaSuccess || cudaMemcpy(ds->blob, bytes, n, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(ds->fst_state2, st2.data(), st2.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(ds->fst_arc4, ar4.data(), ar4.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaMemcpy(ds->fst_arc4, ar4.data(), ar4.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ds->gstate, gst.data(), gst.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ds->garc, gar.data(), gar.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();
     return sttscorer::SCORER_UNREADABLE;
   }
@@ -646,6 +658,11 @@ struct Batch {
   long long launches = 0;
   std::shared_ptr<DeviceScorer> scorer;   // captured by decoder_reset: the scorer this decode / stream runs with
   bool instrument = false;   // decoder statistics build (per-phase clocks, LM counters); bench.py asks for it once
+  // vocabulary pruning of the decoder (get_pruned_emissions); the C API's fixed values (stt.cc:539-540) unless the
+  // decoder-only Python surface sets others
+  double cutoff_prob = 1.0;
+  int cutoff_top_n = 40;
+  uint32_t* d_gen_scratch = nullptr;   // general kernel's per-utterance work arrays, allocated on first use
 };
 
 const StageTimes& batch_times(const Batch* b) { return b->times; }
@@ -796,7 +813,7 @@ void batch_destroy(Batch* b) {
   for (void* p : {(void*)b->d_pcm, (void*)b->d_nsamples, (void*)b->d_feat, (void*)b->d_feat32, (void*)b->d_act_a,
                   (void*)b->d_act_b, (void*)b->d_xw, (void*)b->d_hall, (void*)b->d_c, (void*)b->d_h, (void*)b->d_barrier, (void*)b->d_lstm_prof, (void*)b->d_probs64,
                   (void*)b->d_probs, (void*)b->d_win, (void*)b->d_jobs, (void*)b->d_slot_mem, (void*)b->d_slots,
-                  (void*)b->d_inputs, (void*)b->d_finals, (void*)b->d_out_mem, (void*)b->d_winmat})
+                  (void*)b->d_inputs, (void*)b->d_finals, (void*)b->d_out_mem, (void*)b->d_winmat, (void*)b->d_gen_scratch})
     if (p) cudaFree(p);
   if (b->h_pcm) cudaFreeHost(b->h_pcm);
   if (b->h_nsamples) cudaFreeHost(b->h_nsamples);
@@ -1135,9 +1152,13 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
   if (!make_tmap_2d(&tm_h_out, b->d_hall + (size_t)B * Cp, (uint64_t)M + 128, Cp, Cp, 128)) return -1;
   p.N = Hp; p.K = Cp; p.bias = e->b5; p.out = b->d_act_b;
   if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(tm_h_out, e->tm_w5, p, e->num_sms, st, &e->cfg_mask)) return -1;
-  p.N = 32; p.K = Hp; p.bias = e->b6; p.out = b->d_probs; p.n_valid = m.n_classes;
+  p.N = e->N6; p.K = Hp; p.bias = e->b6; p.out = b->d_probs; p.n_valid = m.n_classes;
   p.out_T_stride = b->T_cap; p.out_t_offset = out_t_offset;
-  if (launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(b->tm_act_b, e->tm_w6, p, e->num_sms, st, &e->cfg_mask)) return -1;
+  if (e->N6 == 32) {
+    if (launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(b->tm_act_b, e->tm_w6, p, e->num_sms, st, &e->cfg_mask)) return -1;
+  } else {
+    if (launch_gemm<256, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(b->tm_act_b, e->tm_w6, p, e->num_sms, st, &e->cfg_mask)) return -1;
+  }
   if (time_it) cudaEventRecord(b->ev[7], st);
   b->launches += 7;
   return 0;
@@ -1223,12 +1244,39 @@ int decoder_reset(Batch* b, int n_slots) {
   return 0;
 }
 
+// Which kernel decodes: the shared-memory kernel covers <= 32 labels, word-mode scorers and no vocabulary pruning (all
+// the C API reaches with the English alphabet); everything else -- wide alphabets, UTF-8 bytes-output scorers, pruning,
+// or merely the sorted class order that cutoff_top_n < classes implies -- runs the general kernel.
+bool needs_general_decoder(const Batch* b) {
+  const int C = (int)b->e->hm.n_classes;
+  const DeviceScorer* sc = b->scorer.get();
+  return C > 33 || (sc && sc->view.is_utf8) || b->cutoff_prob < 1.0 || b->cutoff_top_n < C;
+}
+
 int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& in, int beam) {
   cudaStream_t st = b->st;
   CUDA_OK(cudaMemcpyAsync(b->d_inputs, in.data(), sizeof(sttdec::StepInput) * n_slots, cudaMemcpyHostToDevice, st));
-  const sttdec::DecodeParams dp = make_decode_params(b, beam);
+  sttdec::DecodeParams dp = make_decode_params(b, beam);
   constexpr int NT = 512;
   Engine* e = b->e;
+  if (needs_general_decoder(b)) {
+    if (!b->d_gen_scratch)
+      CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&b->d_gen_scratch),
+                         4ull * sttdec::kGenScratchArrays * (size_t)b->beam_cap * b->B_cap));
+    const DeviceScorer* sc = b->scorer.get();
+    sttdec::GenParams gp{};
+    gp.gstate = sc ? sc->gstate : nullptr;
+    gp.garc = sc ? sc->garc : nullptr;
+    gp.cutoff_prob = b->cutoff_prob;
+    gp.cutoff_top_n = b->cutoff_top_n;
+    gp.scratch = b->d_gen_scratch;
+    dp.fst_space_skip = nullptr;   // the general kernel does not maintain word ordinals: words are hashed
+    dp.ord2wid = nullptr;
+    sttdec::decoder_general_kernel<256><<<n_slots, 256, 0, st>>>(b->d_slots, b->d_inputs, dp, gp);
+    CUDA_OK(cudaGetLastError());
+    b->launches += 1;
+    return 0;
+  }
   auto go = [&](auto kern, int bit, size_t smem) -> int {
     if (ensure_smem(&e->cfg_mask, bit, kern, (int)smem)) return -1;
     kern<<<n_slots, NT, smem, st>>>(b->d_slots, b->d_inputs, dp);
@@ -1236,9 +1284,9 @@ int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& i
   };
   int rc;
   if (b->beam_cap <= 512) {
-    constexpr size_t SM = sizeof(sttdec::StepSmem<512, 3072>);
-    rc = b->instrument ? go(sttdec::decoder_step_kernel<NT, 512, 3072, true>, kBitDec512I, SM)
-                       : go(sttdec::decoder_step_kernel<NT, 512, 3072, false>, kBitDec512, SM);
+    constexpr size_t SM = sizeof(sttdec::StepSmem<512, 5632>);
+    rc = b->instrument ? go(sttdec::decoder_step_kernel<NT, 512, 5632, true>, kBitDec512I, SM)
+                       : go(sttdec::decoder_step_kernel<NT, 512, 5632, false>, kBitDec512, SM);
   } else if (b->beam_cap <= 2048) {
     constexpr size_t SM = sizeof(sttdec::StepSmem<2048, 0>);
     rc = b->instrument ? go(sttdec::decoder_step_kernel<NT, 2048, 0, true>, kBitDec2048I, SM)
@@ -1254,7 +1302,11 @@ int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& i
 }
 
 int decoder_finalize(Batch* b, int n_slots, int beam, int num_results) {
-  const sttdec::DecodeParams dp = make_decode_params(b, beam);
+  sttdec::DecodeParams dp = make_decode_params(b, beam);
+  if (needs_general_decoder(b)) {
+    dp.fst_space_skip = nullptr;
+    dp.ord2wid = nullptr;
+  }
   sttdec::decoder_finalize_kernel<256><<<n_slots, 256, 0, b->st>>>(b->d_slots, b->d_finals, dp, num_results);
   CUDA_OK(cudaGetLastError());
   b->launches += 1;
@@ -1427,6 +1479,13 @@ int batch_lm_stats(Batch* b, unsigned long long* words, unsigned long long* call
     *words += sc[7];
     *calls += sc[8];
   }
+  return 0;
+}
+
+int batch_set_cutoff(Batch* b, double cutoff_prob, int cutoff_top_n) {
+  if (!(cutoff_prob > 0.0) || cutoff_top_n < 1) return -1;
+  b->cutoff_prob = cutoff_prob;
+  b->cutoff_top_n = cutoff_top_n;
   return 0;
 }
 

@@ -52,7 +52,9 @@ void batch_set_instrumented(Batch* b, bool on);              // decoder statisti
 int batch_phase_cycles(Batch* b, unsigned long long* out8);  // instrumentation: summed over utterances
 int batch_lstm_profile(Batch* b, unsigned long long* out3);  // max over CTAs: barrier-wait, load+MMA span, epilogue cycles
 int batch_lm_stats(Batch* b, unsigned long long* words_scored, unsigned long long* lm_calls);  // instrumentation
-int batch_decoder_scalars(Batch* b, unsigned long long* out16);   // sums over the batch of Slot::scalars (decoder.cuh)
+int batch_decoder_scalars(Batch* b, unsigned long long* out16);
+// vocabulary pruning of the following decodes (DecoderState::init's cutoff_prob / cutoff_top_n); C API: 1.0 / 40
+int batch_set_cutoff(Batch* b, double cutoff_prob, int cutoff_top_n);   // sums over the batch of Slot::scalars (decoder.cuh)
 int batch_T(const Batch* b, int utt);                        // timesteps of utterance `utt` after upload
 int batch_copy_features(Batch* b, int utt, float* out);      // [T, n_input] fp32 MFCC
 int batch_copy_probs(Batch* b, int utt, float* out);         // [T, n_classes]

@@ -183,8 +183,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
-      if (EPI == kEpiSoftmaxF32) {
-        static_assert(EPI != kEpiSoftmaxF32 || BLOCK_N == 32, "softmax epilogue expects one 32-column tile");
+      if (EPI == kEpiSoftmaxF32 && BLOCK_N > 32) {
+        // wide alphabets (up to 255 labels + blank, e.g. the UTF-8 bytes-output models): the row does not fit one
+        // 32-column TMEM load, so it is read three times -- maximum, sum of exponentials, normalised write -- with the
+        // same arithmetic, in the same column order, as the one-chunk case below
+        const int t = out_row / p.B, b = out_row % p.B;
+        float* o = static_cast<float*>(p.out) + ((size_t)b * p.out_T_stride + p.out_t_offset + t) * p.n_valid;
+        float mx = -3.4e38f, sum = 0.f, inv = 0.f;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N / 32; ++c) {
+            if (c * 32 >= p.n_valid) break;
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_addr + c * 32, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = c * 32 + j;
+              const float v = __uint_as_float(r[j]) + __ldg(p.bias + col);
+              if (col < p.n_valid) {
+                if (pass == 0) mx = fmaxf(mx, v);
+                else if (pass == 1) sum += expf(v - mx);
+                else if (valid) o[col] = expf(v - mx) * inv;
+              }
+            }
+          }
+          if (pass == 1) inv = 1.0f / sum;
+        }
+      } else if (EPI == kEpiSoftmaxF32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(t_addr, r);
         ptx::tmem_ld_wait();
