@@ -200,6 +200,7 @@ def ref():
         L.ref_scorer_log_cond_prob.restype = c_double
         L.ref_scorer_log_cond_prob.argtypes = [vp, c_char_p, c_int, c_int, c_int]
         L.ref_make_scorer_package.argtypes = [c_char_p, c_char_p, c_int, vp, c_char_p, c_float, c_float]
+        L.ref_make_scorer_package_utf8.argtypes = [c_char_p, c_char_p, c_int, vp, c_char_p, c_float, c_float]
         L.ref_decoder_new.restype = vp
         L.ref_decoder_new.argtypes = [vp, c_int, c_double, c_int, vp, c_char_p, c_void_p, c_int]
         L.ref_decoder_next.argtypes = [vp, c_void_p, c_int, c_int]
@@ -227,6 +228,17 @@ class RefAlphabet(object):
 
     def decode(self, tokens):
         return "".join(self.labels[t] for t in tokens)
+
+
+class RefByteAlphabet(RefAlphabet):
+    """The 255 single-byte labels of UTF8Alphabet (alphabet.h:80-100): label n is the byte n + 1."""
+
+    def __init__(self):
+        self.labels = [bytes([i + 1]) for i in range(255)]
+        self.h = ref().ref_alphabet_from_labels(b"".join(l + b"\0" for l in self.labels), 255)
+
+    def decode(self, tokens):
+        return b"".join(self.labels[t] for t in tokens)
 
 
 class RefScorer(object):

@@ -194,7 +194,7 @@ def _take_metadata(ptr):
     transcripts = []
     for i in range(m.num_transcripts):
         ct = m.transcripts[i]
-        toks = [TokenMetadata(ct.tokens[j].text.decode("utf-8"), ct.tokens[j].timestep, ct.tokens[j].start_time)
+        toks = [TokenMetadata(ct.tokens[j].text.decode("utf-8", errors="surrogateescape"), ct.tokens[j].timestep, ct.tokens[j].start_time)
                 for j in range(ct.num_tokens)]
         transcripts.append(CandidateTranscript(toks, ct.confidence))
     emissions = symbols = None
@@ -203,7 +203,7 @@ def _take_metadata(ptr):
         n = e.num_symbols + 1
         emissions = np.ctypeslib.as_array(e.emissions, shape=(e.num_timesteps, n)).copy() if e.num_timesteps else \
             np.zeros((0, n))
-        symbols = [e.symbols[i].decode("utf-8") for i in range(n)]
+        symbols = [e.symbols[i].decode("utf-8", errors="surrogateescape") for i in range(n)]
     lib().STT_FreeMetadata(ptr)
     return Metadata(transcripts, emissions, symbols)
 

@@ -2,10 +2,9 @@
 (native_client/ctcdecode/__init__.py: Alphabet :17-80, Scorer :82-120, DecodeResult :117-120,
 ctc_beam_search_decoder :122-178, ctc_beam_search_decoder_batch :244-312), executed by the GPU beam search.
 
-Differences: vocabulary pruning is not implemented on the GPU (the C API hard-codes cutoff_prob = 1.0,
-cutoff_top_n = 40, stt.cc:539-540, and the training-side defaults do not prune either), so other values raise;
-`num_processes` is accepted and ignored (utterances are decoded one CTA each); bytes-output (UTF-8) scorers are not
-supported yet.
+`cutoff_prob` / `cutoff_top_n` (vocabulary pruning, get_pruned_emissions), alphabets of up to 255 labels and bytes-output
+(UTF-8) scorers with `UTF8Alphabet` run the general kernel (stt_b200/csrc/decoder_general.cuh); the 28-letter alphabet with
+the defaults runs the shared-memory kernel.  `num_processes` is accepted and ignored (utterances are decoded one CTA each).
 """
 from collections import namedtuple
 
@@ -62,6 +61,34 @@ class Alphabet(object):
         return "".join(self._labels[int(i)] for i in input)
 
 
+class UTF8Alphabet(Alphabet):
+    """Bytes-output mode (native_client/alphabet.h:80-100, ctcdecode/__init__.py:575-627): 255 labels, label n is the
+    single byte n + 1; text is encoded to / decoded from its UTF-8 bytes."""
+
+    def __init__(self):
+        super(UTF8Alphabet, self).__init__()
+        self._labels = [bytes([i + 1]) for i in range(255)]
+        self._index = {l: i for i, l in enumerate(self._labels)}
+
+    def CanEncodeSingle(self, input):
+        return True
+
+    def CanEncode(self, input):
+        return True
+
+    def EncodeSingle(self, input):
+        return self._index[input.encode("utf-8")]
+
+    def Encode(self, input):
+        return [b - 1 for b in input.encode("utf-8")]
+
+    def DecodeSingle(self, input):
+        return self._labels[input].decode("utf-8")
+
+    def Decode(self, input):
+        return b"".join(self._labels[int(i)] for i in input).decode("utf-8", errors="replace")
+
+
 class Scorer(object):
     def __init__(self, alpha=None, beta=None, scorer_path=None, alphabet=None):
         self.alpha, self.beta, self.scorer_path, self.alphabet = alpha, beta, scorer_path, alphabet
@@ -100,8 +127,6 @@ def ctc_beam_search_decoder_batch(probs_seq, seq_lengths, alphabet, beam_size, n
     B, T, C = probs.shape
     if C != alphabet.GetSize() + 1:
         raise ValueError("class dimension must be alphabet size + 1")
-    if cutoff_prob < 1.0 or cutoff_top_n < C:
-        raise NotImplementedError("vocabulary pruning (cutoff_prob < 1 or cutoff_top_n < classes) is not implemented")
     m = _host(alphabet, scorer)
     m.setBeamWidth(beam_size)
     lib = api.lib()
@@ -113,6 +138,7 @@ def ctc_beam_search_decoder_batch(probs_seq, seq_lengths, alphabet, beam_size, n
         n = min(256, B - base)
         bt = m.createBatch(n, max(T, 1) * 320 + 512)
         bt.set_probs64(probs[base:base + n], np.asarray(seq_lengths[base:base + n], np.int32))
+        bt.set_cutoff(cutoff_prob, cutoff_top_n)
         bt.decode(num_results)
         bt.fetch()
         for u in range(n):

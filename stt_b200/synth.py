@@ -14,7 +14,7 @@ def serialize_alphabet(labels):
     """Alphabet::Serialize format (native_client/alphabet.cc:101-125)."""
     out = struct.pack("<H", len(labels))
     for i, l in enumerate(labels):
-        b = l.encode("utf-8")
+        b = l if isinstance(l, bytes) else l.encode("utf-8")   # bytes-output alphabets hold raw single bytes
         out += struct.pack("<HH", i, len(b)) + b
     return out
 

@@ -36,5 +36,7 @@ def test_ctcdecoder_batch_matches_reference(ref_decoder, vocab_words, english):
     rs.set_alpha_beta(0.75, 1.85)
     rc, rt, rts = o.ref_decode(probs[0], ra, 64, rs)[0]
     assert one[0].tokens == list(rt) and one[0].confidence == rc
-    with pytest.raises(NotImplementedError):
-        ctcdecoder.ctc_beam_search_decoder(probs[0], alpha, 8, cutoff_prob=0.99)
+    # vocabulary pruning runs the general kernel
+    pruned = ctcdecoder.ctc_beam_search_decoder(probs[0], alpha, 8, cutoff_prob=0.99, cutoff_top_n=5, scorer=ctcdecoder.Scorer(0.75, 1.85, SCORER, alpha))
+    rc, rt, rts = o.ref_decode(probs[0], ra, 8, rs, cutoff_prob=0.99, cutoff_top_n=5)[0]
+    assert pruned[0].tokens == list(rt) and pruned[0].timesteps == list(rts) and pruned[0].confidence == rc

@@ -1,0 +1,223 @@
+"""The general beam-search kernel (stt_b200/csrc/decoder_general.cuh) against the GENUINE reference decoder, bit-exact
+(tokens, timesteps, confidence), on everything the shared-memory kernel does not cover:
+  * vocabulary pruning, get_pruned_emissions (ctc_beam_search_decoder.cpp:328-358): cutoff_prob < 1, cutoff_top_n, and
+    the sorted class order that cutoff_top_n < classes alone already implies (the blank no longer comes last);
+  * alphabets of 100 and 255 labels, with and without pruning;
+  * bytes-output (UTF-8) scorers: the reference's own fixture data/smoke_test/pruned_lm.bytes.scorer (ASCII) and a
+    multilingual one with 2-, 3- and 4-byte code points (tests/golden/make_bytes_scorer.py), hot words included;
+  * a bytes-output MODEL (256 classes: wide softmax epilogue) end to end through the C API with the bytes scorer."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SCORER
+
+pytestmark = pytest.mark.gpu
+BYTES_SMOKE = os.path.join(GOLDEN, "bytes", "pruned_lm.bytes.scorer")
+BYTES_MULTI = os.path.join(GOLDEN, "bytes", "multilingual.bytes.scorer")
+BYTE_LABELS = [bytes([i + 1]) for i in range(255)]
+
+
+def _same(g, r):
+    (gc, gt, gts), (rc, rt, rts) = g, r
+    return list(gt) == list(rt) and list(gts) == list(rts) and gc == rc
+
+
+def _host_model(labels, scorer=None, beam=100):
+    from stt_b200 import Model, synth
+    w = synth.make_weights(n_hidden=16, n_classes=len(labels) + 1, seed=0)
+    m = Model(synth.model_bytes(w, labels=labels, beam_width=beam))
+    if scorer:
+        m.enableExternalScorer(scorer)
+    return m
+
+
+def _gpu_decode(m, probs, lens, beam, num_results, cutoff_prob, cutoff_top_n):
+    m.setBeamWidth(beam)
+    B, T, C = probs.shape
+    b = m.createBatch(B, max(T, 1) * 320 + 512)
+    b.set_probs(probs, lens)
+    b.set_cutoff(cutoff_prob, cutoff_top_n)
+    b.decode(num_results)
+    b.fetch()
+    return [b.results(u) for u in range(B)]
+
+
+def _compare(o, m, ra, rs, probs, lens, beam, num_results=3, cutoff_prob=1.0, cutoff_top_n=40, what=""):
+    got = _gpu_decode(m, probs, lens, beam, num_results, cutoff_prob, cutoff_top_n)
+    ref = o.ref_decode_batch(probs.astype(np.float64), lens, ra, beam, rs, num_processes=os.cpu_count() or 8,
+                             num_results=num_results, cutoff_prob=cutoff_prob, cutoff_top_n=cutoff_top_n)
+    bad = []
+    for u in range(len(lens)):
+        ok = len(got[u]) == len(ref[u])
+        for g, r in zip(got[u], ref[u]):
+            if r[0] <= -3.0e38 and g[0] == r[0]:
+                # a prefix that never got a finite score ("zombie", score -FLT_MAX): which of several such prefixes the
+                # reference's nth_element / sort leaves first is unspecified (DESIGN, tie caveat); only the score is compared
+                continue
+            ok = ok and _same(g, r)
+        if not ok:
+            bad.append(u)
+    assert not bad, "%s beam %d cutoff (%g, %d): %d/%d utterances differ from the reference, first %s:\n got %s\n ref %s" % (
+        what, beam, cutoff_prob, cutoff_top_n, len(bad), len(lens), bad[:5],
+        [(c, [int(x) for x in t], [int(x) for x in ts]) for c, t, ts in got[bad[0]]],
+        [(float(c), [int(x) for x in t], [int(x) for x in ts]) for c, t, ts in ref[bad[0]]])
+    return got
+
+
+def _ctc_rows(seq, C, rng, noise=0.02, blank_p=0.9, confuse=None):
+    """One emitting frame + 1-2 blank frames per label of `seq`; Dirichlet-ish noise over C classes."""
+    rows = []
+    for lab in seq:
+        r = rng.gamma(0.3, 1.0, size=C) * noise
+        r[lab] += rng.uniform(0.5, 0.95)
+        if confuse is not None and rng.random() < 0.5:
+            r[int(confuse[rng.integers(len(confuse))])] += rng.uniform(0.05, 0.4)
+        rows.append(r / r.sum())
+        for _ in range(int(rng.integers(1, 3))):
+            r = rng.gamma(0.3, 1.0, size=C) * noise
+            r[C - 1] += blank_p
+            rows.append(r / r.sum())
+    return rows
+
+
+def _batch(seqs, C, rng, **kw):
+    rows = [_ctc_rows(s, C, rng, **kw) for s in seqs]
+    T = max(len(r) for r in rows)
+    probs = np.zeros((len(rows), T, C), np.float32)
+    lens = []
+    for u, r in enumerate(rows):
+        probs[u, :len(r)] = np.asarray(r, np.float32)
+        lens.append(len(r))
+    return probs, lens
+
+
+@pytest.mark.parametrize("scorer", [True, False])
+def test_pruning_english_alphabet(ref_decoder, vocab_words, english, scorer):
+    from stt_b200 import synth
+    o = ref_decoder
+    ra = o.RefAlphabet(english)
+    rs = o.RefScorer(SCORER, ra) if scorer else None
+    m = _host_model(english, SCORER if scorer else None)
+    B, T = 12, 80
+    probs = np.stack([synth.make_ctc_probs(vocab_words, T, utt=9100 + u, noise=[0.02, 0.08, 0.2][u % 3]) for u in range(B)])
+    lens = [T, 60, T, 1, 33, T, T, 17, T, T, 2, T]
+    for beam in (1, 16, 100, 500):
+        for cp, tn in ((0.99, 40), (0.9, 40), (0.999, 5), (1.0, 10), (0.5, 3), (0.99, 1)):
+            _compare(o, m, ra, rs, probs, lens, beam, 3, cp, tn, "english scorer=%s" % scorer)
+
+
+@pytest.mark.parametrize("n_labels", [100, 255])
+def test_wide_alphabets_without_scorer(ref_decoder, n_labels):
+    o = ref_decoder
+    labels = ["<%d>" % i for i in range(n_labels)]
+    labels[7] = " "
+    ra = o.RefAlphabet(labels)
+    m = _host_model(labels)
+    C = n_labels + 1
+    rng = np.random.default_rng(77 + n_labels)
+    seqs = [rng.integers(0, n_labels, size=int(rng.integers(1, 40))) for _ in range(10)]
+    probs, lens = _batch(seqs, C, rng, noise=0.05, confuse=np.arange(n_labels))
+    flat = rng.dirichlet(np.ones(C) * 0.5, size=(2, probs.shape[1])).astype(np.float32)   # flat rows: wide beams of near-ties
+    probs = np.concatenate([probs, flat])
+    lens += [probs.shape[1], 9]
+    for beam in (1, 20, 300):
+        for cp, tn in ((1.0, 40), (1.0, 1000), (0.99, 40), (0.8, 10)):
+            _compare(o, m, ra, None, probs, lens, beam, 2, cp, tn, "%d labels" % n_labels)
+
+
+def _byte_seqs(texts):
+    return [[b - 1 for b in t.encode("utf-8")] for t in texts]
+
+
+def test_bytes_mode_reference_fixture(ref_decoder):
+    """data/smoke_test/pruned_lm.bytes.scorer with the 255-label UTF8Alphabet."""
+    o = ref_decoder
+    ra = o.RefByteAlphabet()
+    rs = o.RefScorer(BYTES_SMOKE, ra)
+    assert o.ref().ref_scorer_is_utf8(rs.h) == 1
+    m = _host_model(BYTE_LABELS, BYTES_SMOKE)
+    words = open(os.path.join(GOLDEN, "bytes", "vocab.pruned.bytes.head.txt")).read().split("\n")[:-1]
+    rng = np.random.default_rng(5)
+    texts = ["".join(words[int(rng.integers(len(words)))].replace(" ", "") for _ in range(int(rng.integers(1, 5)))) for _ in range(10)]
+    probs, lens = _batch(_byte_seqs(texts), 256, rng, noise=0.03, confuse=np.arange(ord("a") - 1, ord("z")))
+    for beam in (1, 8, 100, 500):
+        for cp, tn in ((1.0, 40), (1.0, 256), (0.99, 40), (0.9, 6)):
+            _compare(o, m, ra, rs, probs, lens, beam, 3, cp, tn, "bytes smoke")
+    for a, be in ((0.5, 2.0), (2.0, 0.1)):
+        rs.set_alpha_beta(a, be)
+        m.setScorerAlphaBeta(a, be)
+        _compare(o, m, ra, rs, probs, lens, 64, 2, 1.0, 40, "bytes smoke alpha %g" % a)
+
+
+def test_bytes_mode_multibyte_code_points(ref_decoder):
+    o = ref_decoder
+    ra = o.RefByteAlphabet()
+    rs = o.RefScorer(BYTES_MULTI, ra)
+    m = _host_model(BYTE_LABELS, BYTES_MULTI)
+    sentences = open(os.path.join(GOLDEN, "bytes", "multilingual.txt"), encoding="utf-8").read().split("\n")[:-1]
+    rng = np.random.default_rng(11)
+    texts = [s.replace(" ", "") for s in sentences] + ["niño😀日本", "ßü🚀", "é", "😀"]
+    all_bytes = np.array(sorted({b - 1 for t in texts for b in t.encode("utf-8")}))
+    probs, lens = _batch(_byte_seqs(texts), 256, rng, noise=0.02, confuse=all_bytes)
+    for beam in (1, 8, 100, 500):
+        for cp, tn in ((1.0, 40), (1.0, 256), (0.99, 40)):
+            got = _compare(o, m, ra, rs, probs, lens, beam, 3, cp, tn, "bytes multilingual")
+    best = b"".join(BYTE_LABELS[t] for t in got[0][0][1]).decode("utf-8", errors="replace")
+    assert len(best) > 3, best   # the decode really emits multi-byte text
+
+
+def test_bytes_mode_python_surface(ref_decoder):
+    """ctcdecoder.UTF8Alphabet + Scorer through ctc_beam_search_decoder_batch, pruning arguments passed through."""
+    from stt_b200 import ctcdecoder
+    o = ref_decoder
+    ra = o.RefByteAlphabet()
+    rs = o.RefScorer(BYTES_MULTI, ra)
+    rs.set_alpha_beta(0.8, 1.3)
+    alpha = ctcdecoder.UTF8Alphabet()
+    assert alpha.GetSize() == 255 and alpha.Decode(alpha.Encode("größe 😀")) == "größe 😀"
+    sc = ctcdecoder.Scorer(0.8, 1.3, BYTES_MULTI, alpha)
+    rng = np.random.default_rng(13)
+    probs, lens = _batch(_byte_seqs(["日本語のテスト", "caféaulait", "😀🚀"]), 256, rng, noise=0.02)
+    probs = probs.astype(np.float64)
+    for cp, tn in ((1.0, 40), (0.98, 20)):
+        got = ctcdecoder.ctc_beam_search_decoder_batch(probs, lens, alpha, 50, cutoff_prob=cp, cutoff_top_n=tn, scorer=sc,
+                                                       num_results=2)
+        ref = o.ref_decode_batch(probs, lens, ra, 50, rs, num_processes=2, num_results=2, cutoff_prob=cp, cutoff_top_n=tn)
+        for u in range(3):
+            assert len(got[u]) == len(ref[u])
+            for g, (rc, rt, rts) in zip(got[u], ref[u]):
+                assert g.tokens == list(rt) and g.timesteps == list(rts) and g.confidence == rc
+
+
+def test_bytes_output_model_end_to_end(oracle, ref_decoder):
+    """A 256-class acoustic model (wide softmax epilogue) through STT_* with the bytes scorer: probabilities against
+    the oracle, transcript against the reference decoder run on the GPU's probabilities with the C API's fixed
+    cutoff_prob = 1.0 / cutoff_top_n = 40 (stt.cc:539-540), which for 256 classes means the sorted class order."""
+    from stt_b200 import Model, synth
+    o = ref_decoder
+    w = synth.make_weights(n_hidden=64, n_classes=256, seed=4)
+    m = Model(synth.model_bytes(w, labels=BYTE_LABELS, beam_width=50))
+    pcm = synth.make_pcm(32000, utt=3)
+    b = m.createBatch(1, pcm.size)
+    b.upload([pcm])
+    b.forward()
+    probs = b.probs(0)
+    assert probs.shape[1] == 256
+    am = oracle.PortAM(w)
+    ref_p, _ = am.stream(pcm)
+    assert ref_p.shape == probs.shape
+    assert float(np.abs(probs - ref_p).max()) <= 2e-3
+    np.testing.assert_allclose(probs.sum(1), 1.0, rtol=1e-4)
+    ra = o.RefByteAlphabet()
+    for scorer in (None, BYTES_SMOKE):
+        if scorer:
+            m.enableExternalScorer(scorer)
+        rs = o.RefScorer(scorer, ra) if scorer else None
+        md = m.sttWithMetadata(pcm, 2)
+        ref = o.ref_decode(probs, ra, 50, rs, num_results=2, cutoff_prob=1.0, cutoff_top_n=40)
+        assert len(md.transcripts) == len(ref)
+        for t, (rc, rt, rts) in zip(md.transcripts, ref):
+            assert [x.timestep for x in t.tokens] == list(rts) and t.confidence == rc
+            assert b"".join(BYTE_LABELS[i] for i in rt) == b"".join(x.text.encode("utf-8", "surrogateescape") for x in t.tokens)
