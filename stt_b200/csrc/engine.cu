@@ -20,6 +20,7 @@
 #include "decoder.cuh"
 #include "decoder_general.cuh"
 #include "gemm_tc.cuh"
+#include "gemm2_tc.cuh"
 #include "lstm2_tc.cuh"
 #include "probe_tc.cuh"
 #include "lstm_tc.cuh"
@@ -111,7 +112,7 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
 // Kernel attributes (opt-in shared memory) are per DEVICE: each Engine remembers which of its kernels it has configured
 // on its device in a bit mask.  Setting an attribute twice is harmless, so concurrent host threads need no lock.
 enum KernelBit {
-  kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitGemmSoftmaxWide, kBitDecGeneral, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
+  kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitGemmSoftmaxWide, kBitDecGeneral, kBitGemm2Relu, kBitGemm2Bias, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
   kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitDec512, kBitDec512I, kBitDec2048, kBitDec2048I
 };
 template <class K>
@@ -143,6 +144,30 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::Gem
   const int grid = std::max(1, std::min(n_tiles, num_sms));
   kern<<<grid, sttgemm::kNumThreads, L::kTotal, st>>>(ta, tb, p);
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// CTA-pair 256 x 256 tiles (gemm2_tc.cuh) for the layers whose N is a multiple of 256; tb must have 128-row boxes.
+template <int EPI>
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::GemmParams& p, int num_sms, cudaStream_t st,
+                 std::atomic<uint32_t>* cfg_mask) {
+  constexpr int STAGES = 6;
+  using L = sttgemm::Smem2Layout<STAGES>;
+  auto kern = sttgemm::gemm2_tc_kernel<STAGES, EPI>;
+  if (ensure_smem(cfg_mask, EPI == sttgemm::kEpiClipReluF16 ? kBitGemm2Relu : kBitGemm2Bias, kern, L::kTotal)) return -1;
+  const int n_tiles = ((p.M + 255) / 256) * (p.N / 256);
+  const int pairs = std::max(1, std::min(n_tiles, num_sms / 2));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(sttgemm::kNumThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return 0;
 }
 
@@ -183,6 +208,8 @@ struct Engine {
   __half *w1 = nullptr, *w2 = nullptr, *w3 = nullptr, *wx = nullptr, *wh = nullptr, *w5 = nullptr, *w6 = nullptr;
   float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr, *bx = nullptr, *b5 = nullptr, *b6 = nullptr;
   CUtensorMap tm_w1, tm_w2, tm_w3, tm_wx, tm_wh, tm_w5, tm_w6;
+  CUtensorMap tm_w2h, tm_w3h, tm_wxh, tm_w5h;   // the same weights with 128-row boxes (CTA-pair GEMM: each CTA stages half a tile)
+  int opt_gemm_pair = 1;
   // MFCC tables
   sttmfcc::MfccTables tables{};
   std::vector<void*> table_allocs;
@@ -340,7 +367,9 @@ int build_weights(Engine* e) {
   bool ok = make_tmap_2d(&e->tm_w1, e->w1, Hp, K1p, K1p, 256) && make_tmap_2d(&e->tm_w2, e->w2, Hp, Hp, Hp, 256) &&
             make_tmap_2d(&e->tm_w3, e->w3, Hp, Hp, Hp, 256) && make_tmap_2d(&e->tm_wx, e->wx, 4 * Cp, Hp, Hp, 256) &&
             make_tmap_2d(&e->tm_wh, e->wh, 4 * Cp, Cp, Cp, 64) && make_tmap_2d(&e->tm_w5, e->w5, Hp, Cp, Cp, 256) &&
-            make_tmap_2d(&e->tm_w6, e->w6, e->N6, Hp, Hp, e->N6);
+            make_tmap_2d(&e->tm_w6, e->w6, e->N6, Hp, Hp, e->N6) &&
+            make_tmap_2d(&e->tm_w2h, e->w2, Hp, Hp, Hp, 128) && make_tmap_2d(&e->tm_w3h, e->w3, Hp, Hp, Hp, 128) &&
+            make_tmap_2d(&e->tm_wxh, e->wx, 4 * Cp, Hp, Hp, 128) && make_tmap_2d(&e->tm_w5h, e->w5, Hp, Cp, Cp, 128);
   return ok ? 0 : -1;
 }
 
@@ -363,6 +392,7 @@ Engine* engine_create(const sttmodel::HostModel& m, std::string* err) {
     e->opt_word_ordinals = getenv("STT_B200_NO_WORD_ORDINALS") ? 0 : 1;
     e->opt_dec_flags = geti("STT_B200_DEC_FLAGS", e->opt_dec_flags);
     e->opt_lstm_exact_h = geti("STT_B200_LSTM_EXACT_H", 1);
+    e->opt_gemm_pair = geti("STT_B200_GEMM_PAIR", 1);
     e->verbose = getenv("STT_B200_VERBOSE") != nullptr;
     // A CUDA injection library (Nsight Compute / Systems) serialises kernels and, with this driver, fails launches that
     // carry BOTH the cooperative and the cluster attribute; see launch_lstm_*.
@@ -1126,14 +1156,18 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
     CUDA_OK(cudaGetLastError());
     if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_winmat, e->tm_w1, p, e->num_sms, st, &e->cfg_mask)) return -1;
   }
+  const bool pairs = e->opt_gemm_pair != 0;
   p.K = Hp; p.bias = e->b2; p.out = b->d_act_b;
-  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_a, e->tm_w2, p, e->num_sms, st, &e->cfg_mask)) return -1;
+  if (pairs ? launch_gemm2<sttgemm::kEpiClipReluF16>(b->tm_act_a, e->tm_w2h, p, e->num_sms, st, &e->cfg_mask)
+            : launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_a, e->tm_w2, p, e->num_sms, st, &e->cfg_mask)) return -1;
   p.bias = e->b3; p.out = b->d_act_a;
-  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_b, e->tm_w3, p, e->num_sms, st, &e->cfg_mask)) return -1;
+  if (pairs ? launch_gemm2<sttgemm::kEpiClipReluF16>(b->tm_act_b, e->tm_w3h, p, e->num_sms, st, &e->cfg_mask)
+            : launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(b->tm_act_b, e->tm_w3, p, e->num_sms, st, &e->cfg_mask)) return -1;
   if (time_it) cudaEventRecord(b->ev[4], st);
   // ---- hoisted input half of the LSTM matmul (+ bias)
   p.N = 4 * Cp; p.K = Hp; p.bias = e->bx; p.out = b->d_xw;
-  if (launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(b->tm_act_a, e->tm_wx, p, e->num_sms, st, &e->cfg_mask)) return -1;
+  if (pairs ? launch_gemm2<sttgemm::kEpiBiasF32>(b->tm_act_a, e->tm_wxh, p, e->num_sms, st, &e->cfg_mask)
+            : launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(b->tm_act_a, e->tm_wx, p, e->num_sms, st, &e->cfg_mask)) return -1;
   if (time_it) cudaEventRecord(b->ev[5], st);
   // ---- recurrence
   {
@@ -1151,7 +1185,8 @@ int run_am(Batch* b, int B, int T, int out_t_offset, bool time_it) {
   CUtensorMap tm_h_out;
   if (!make_tmap_2d(&tm_h_out, b->d_hall + (size_t)B * Cp, (uint64_t)M + 128, Cp, Cp, 128)) return -1;
   p.N = Hp; p.K = Cp; p.bias = e->b5; p.out = b->d_act_b;
-  if (launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(tm_h_out, e->tm_w5, p, e->num_sms, st, &e->cfg_mask)) return -1;
+  if (pairs ? launch_gemm2<sttgemm::kEpiClipReluF16>(tm_h_out, e->tm_w5h, p, e->num_sms, st, &e->cfg_mask)
+            : launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(tm_h_out, e->tm_w5, p, e->num_sms, st, &e->cfg_mask)) return -1;
   p.N = e->N6; p.K = Hp; p.bias = e->b6; p.out = b->d_probs; p.n_valid = m.n_classes;
   p.out_T_stride = b->T_cap; p.out_t_offset = out_t_offset;
   if (e->N6 == 32) {

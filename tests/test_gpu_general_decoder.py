@@ -221,3 +221,57 @@ def test_bytes_output_model_end_to_end(oracle, ref_decoder):
         for t, (rc, rt, rts) in zip(md.transcripts, ref):
             assert [x.timestep for x in t.tokens] == list(rts) and t.confidence == rc
             assert b"".join(BYTE_LABELS[i] for i in rt) == b"".join(x.text.encode("utf-8", "surrogateescape") for x in t.tokens)
+
+
+def _ref_decode_hot(o, probs, T, ra, rs, beam, hot, num_results, cutoff_prob, cutoff_top_n):
+    R = o.ref()
+    words = b"".join((w if isinstance(w, bytes) else w.encode("utf-8")) + b"\0" for w in hot)
+    boosts = np.array(list(hot.values()), np.float32)
+    d = R.ref_decoder_new(ra.h, beam, cutoff_prob, cutoff_top_n, rs.h, words, boosts.ctypes.data, len(hot))
+    p64 = np.ascontiguousarray(probs[:T], np.float64)
+    R.ref_decoder_next(d, p64.ctypes.data, T, p64.shape[1])
+    conf = np.zeros(num_results, np.float64)
+    nt = np.zeros(num_results, np.int32)
+    tok = np.zeros((num_results, T), np.uint32)
+    ts = np.zeros((num_results, T), np.uint32)
+    n = R.ref_decoder_decode(d, num_results, T, conf.ctypes.data, nt.ctypes.data, tok.ctypes.data, ts.ctypes.data)
+    R.ref_decoder_free(d)
+    return [(conf[r], tok[r, :nt[r]], ts[r, :nt[r]]) for r in range(n)]
+
+
+def test_hot_words_in_the_general_kernel(ref_decoder, vocab_words, english):
+    """ctc_beam_search_decoder.cpp:224-239 in both scorer modes of the general kernel: code points as hot "words" with the
+    multilingual bytes scorer, and ordinary hot words under vocabulary pruning with the English scorer."""
+    from stt_b200 import synth
+    o = ref_decoder
+    # ---- UTF-8 mode
+    ra = o.RefByteAlphabet()
+    rs = o.RefScorer(BYTES_MULTI, ra)
+    m = _host_model(BYTE_LABELS, BYTES_MULTI)
+    hot = {"é": 6.5, "日": -3.0, "😀": 4.25, "q": 2.0, "notaunit": 9.0}
+    for w, b in hot.items():
+        m.addHotWord(w, b)
+    rng = np.random.default_rng(21)
+    texts = ["cafédéjàvu", "日本語のテスト", "smile😀rocket🚀", "quick"]
+    probs, lens = _batch(_byte_seqs(texts), 256, rng, noise=0.03)
+    for beam, cp, tn in ((50, 1.0, 40), (200, 0.99, 30)):
+        got = _gpu_decode(m, probs, lens, beam, 2, cp, tn)
+        for u in range(len(texts)):
+            ref = _ref_decode_hot(o, probs[u], lens[u], ra, rs, beam, hot, 2, cp, tn)
+            assert len(got[u]) == len(ref)
+            for g, r in zip(got[u], ref):
+                assert _same(g, r), ("utf8 hot words", beam, u, g, r)
+    # ---- word mode under pruning
+    ra = o.RefAlphabet(english)
+    rs = o.RefScorer(SCORER, ra)
+    m = _host_model(english, SCORER)
+    hot = {"the": 7.5, "and": -4.0, vocab_words[10]: 6.0, vocab_words[200]: -2.5}
+    for w, b in hot.items():
+        m.addHotWord(w, b)
+    T = 120
+    probs = np.stack([synth.make_ctc_probs(vocab_words, T, utt=5150 + u) for u in range(3)])
+    got = _gpu_decode(m, probs, [T] * 3, 100, 2, 0.995, 12)
+    for u in range(3):
+        ref = _ref_decode_hot(o, probs[u], T, ra, rs, 100, hot, 2, 0.995, 12)
+        for g, r in zip(got[u], ref):
+            assert _same(g, r), ("pruned hot words", u, g, r)
