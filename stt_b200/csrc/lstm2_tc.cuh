@@ -297,12 +297,39 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorM
       : "memory");
 }
 
-// tmap_h / tmap_wh: 3-D maps {64 columns, rows, K block} with box {64, 64, KB}.  Launch: cooperative, cluster (2,1,1).
+// The same load delivered to every CTA of `cta_mask` (same shared-memory offset in each); with cta_group::2 the bytes
+// are accounted on the mbarrier at this offset in the EVEN CTA of each destination's pair, which is why the barrier
+// address has the peer bit cleared (the convention of CUTLASS's SM100_TMA_2SM_LOAD_MULTICAST).
+__device__ __forceinline__ void tma_load_3d_pair_mcast(void* smem_dst, const CUtensorMap* m, uint32_t mbar_addr, int c0, int c1,
+                                                       int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_addr), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_mask(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the bit that tells the two CTAs of a pair apart in a shared::cluster address
+
+// tmap_h / tmap_wh: 3-D maps {64 columns, rows, K block} with box {64, 64, KB}.  Launch: cooperative, cluster (CS,1,1).
 // p.barrier: 2 groups x kPPCounters counters, 128 B apart, zero-initialised.
-template <int KB, int STAGES>
+//
+// CS = 8 (needs KB = 4; tmap_h then has box {64, 64, 1}): the kernel is bound by what L2 can deliver -- 128 CTAs x 1 MB
+// per step = 128 MB / 21.5 k cycles = 5.9 KB/clk, the measured ceiling of the L2 slices -- and half of that is the SAME h
+// rows fetched by all 64 pairs.  Four pairs share a cluster: each CTA fetches ONE of the four K blocks of its 64 rows
+// and multicasts it to the four CTAs of its parity, so a step reads h 16 times instead of 64 (80 MB instead of 128).
+// A stage is refilled when all four pairs have consumed it (every pair leader's commit arrives in all eight CTAs).
+template <int KB, int STAGES, int CS = 2>
 __global__ void __launch_bounds__(kPPThreads, 1)
 lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_wh,
                const LstmParams p) {
+  static_assert(CS == 2 || (CS == 8 && KB == 4), "multicast variant: one K block per pair of the cluster");
   using L = PPSmem<KB, STAGES>;
   constexpr int kPPStages = STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -315,7 +342,9 @@ lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const int num_k_blocks = (p.n_cell / BLOCK_K + KB - 1) / KB;   // in units of KB K blocks (a short tail is zero-filled by TMA)
-  const uint32_t crank = ptx::cluster_ctarank();       // 0 = leader
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t crank = rank & 1u;                    // 0 = leader of its pair
+  const uint32_t qpair = rank >> 1;                    // pair within the cluster
   const int pair = blockIdx.x >> 1;
   const int n0 = pair * kPairN;                        // first gate column of the pair
   const int n_groups = (p.B + 127) / 128;              // 1 or 2
@@ -327,7 +356,7 @@ lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
     ptx::prefetch_tmap(&tmap_wh);
     for (int i = 0; i < kPPStages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], CS / 2);   // one commit per pair of the cluster
     }
     ptx::mbar_init(&tmem_full_bar[0], 1);
     ptx::mbar_init(&tmem_full_bar[1], 1);
@@ -373,13 +402,19 @@ lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
           const int row0 = t * p.B + g * 128 + (int)crank * 64;
           for (int kb = 0; kb < num_k_blocks; ++kb) {
             uint8_t* sa = smem + stage * L::kStageBytes;
-            const uint32_t leader_full = mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+            const uint32_t leader_full = ptx::smem_u32(&full_bar[stage]) & kPeerBitMask;   // the pair leader's barrier
             // No weight prefetch ahead of the barrier here: the other group's MMAs keep the ring busy until its last
             // stages drain, and by then this group's barrier has normally completed.
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             if (crank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);  // both CTAs' halves
             tma_load_3d_pair(sa + L::kABytes, &tmap_wh, leader_full, 0, n0 + (int)crank * 64, kb * KB);
-            tma_load_3d_pair(sa, &tmap_h, leader_full, 0, row0, kb * KB);
+            if (CS == 2) {
+              tma_load_3d_pair(sa, &tmap_h, leader_full, 0, row0, kb * KB);
+            } else {
+              // this CTA's K block of the 64 rows, for the four CTAs of its parity in the cluster
+              tma_load_3d_pair_mcast(sa + qpair * L::kTile, &tmap_h, leader_full, 0, row0, kb * KB + (int)qpair,
+                                     crank ? (uint16_t)0xAA : (uint16_t)0x55);
+            }
             if (++stage == kPPStages) { stage = 0; phase ^= 1; }
           }
           prof_main += (unsigned long long)(clock64() - q1);
@@ -418,8 +453,13 @@ lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                   umma_f16_pair(acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | i | k) != 0);
               }
-              umma_commit_pair(&empty_bar[stage]);
-              if (kb == num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[g]);
+              if (CS == 2) {
+                umma_commit_pair(&empty_bar[stage]);
+                if (kb == num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[g]);
+              } else {
+                umma_commit_pair_mask(&empty_bar[stage], (uint16_t)0xFF);          // every CTA's producer counts this pair
+                if (kb == num_k_blocks - 1) umma_commit_pair_mask(&tmem_full_bar[g], (uint16_t)(3u << (2 * qpair)));
+              }
             }
             __syncwarp();
             if (++stage == kPPStages) { stage = 0; phase ^= 1; }
