@@ -113,7 +113,7 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
 // on its device in a bit mask.  Setting an attribute twice is harmless, so concurrent host threads need no lock.
 enum KernelBit {
   kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitGemmSoftmaxWide, kBitDecGeneral, kBitGemm2Relu, kBitGemm2Bias, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
-  kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitLstmPP4Mc, kBitDec512, kBitDec512I, kBitDec2048, kBitDec2048I
+  kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitLstmPP4Mc, kBitLstmPP4Mc4, kBitDec512, kBitDec512I, kBitDec2048, kBitDec2048I
 };
 template <class K>
 int ensure_smem(std::atomic<uint32_t>* mask, int bit, K kern, int bytes) {
@@ -218,7 +218,7 @@ struct Engine {
   std::atomic<uint32_t> cfg_mask{0};   // KernelBit: kernels whose attributes are set on this device
   std::mutex launch_mu;                // guards the caches below
   std::map<std::pair<int, int>, int> lstm_cluster;   // (M tiles, grid) -> cluster size that is co-resident
-  int lstm_pair_usable = -1, lstm_pp_usable[4] = {-1, -1, -1, -1};
+  int lstm_pair_usable = -1, lstm_pp_usable[5] = {-1, -1, -1, -1, -1};
   bool use_overlap_view = true;
   bool lstm_noncoop = false;           // see launch_lstm_pp_inst
   // ---- options, read ONCE when the engine is created (development switches; none is needed in production)
@@ -1068,15 +1068,18 @@ int launch_lstm_pp_inst(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaS
   Engine* e = b->e;
   using L = sttlstm::PPSmem<KB, STAGES>;
   auto kern = sttlstm::lstm_pp_kernel<KB, STAGES, CS>;
-  constexpr int idx = CS == 8 ? 3 : KB == 4 ? 0 : KB == 2 ? 1 : 2;
-  if (CS == 8 && grid % 8 != 0) return 1;
+  constexpr int idx = CS == 8 ? 3 : CS == 4 ? 4 : KB == 4 ? 0 : KB == 2 ? 1 : 2;
+  if (grid % CS != 0) return 1;
   {
     std::lock_guard<std::mutex> lk(e->launch_mu);
     if (e->lstm_pp_usable[idx] < 0) {
       e->lstm_pp_usable[idx] = 0;
       if (ensure_smem(&e->cfg_mask, kBitLstmPP4 + idx, kern, L::kTotal) == 0)
-        e->lstm_pp_usable[idx] = resident_ctas(e, kern, sttlstm::kPPThreads, L::kTotal, grid, CS) >= grid ? 1 : 0;
-      if (e->verbose) fprintf(stderr, "[stt_b200] LSTM ping-pong kernel<%d,%d,cluster %d> usable=%d\n", KB, STAGES, CS, e->lstm_pp_usable[idx]);
+      {
+        const long long res = resident_ctas(e, kern, sttlstm::kPPThreads, L::kTotal, grid, CS);
+        e->lstm_pp_usable[idx] = res >= grid ? 1 : 0;
+        if (e->verbose) fprintf(stderr, "[stt_b200] LSTM ping-pong kernel<%d,%d,cluster %d>: %lld CTAs can be resident, %d needed\n", KB, STAGES, CS, res, grid);
+      }
     }
     if (!e->lstm_pp_usable[idx]) return 1;
   }
@@ -1092,7 +1095,7 @@ int launch_lstm_pp_inst(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaS
     const uint64_t rows = (uint64_t)b->T_cap * b->B_cap + b->B_cap + 256;
     uint64_t dims[3] = {64, rows, (uint64_t)(Cp / 64)};
     uint64_t strides[2] = {(uint64_t)Cp * 2, 128};
-    uint32_t box[3] = {64, 64, (uint32_t)(CS == 8 ? 1 : KB)};   // multicast variant: one K block per request
+    uint32_t box[3] = {64, 64, (uint32_t)(KB * 2 / CS)};   // multicast variant: this CTA's share of the K blocks
     if (!make_tmap(&tm_h, b->d_hall, 3, dims, strides, box)) return 1;
     dims[1] = (uint64_t)4 * Cp;
     box[2] = (uint32_t)KB;
@@ -1107,6 +1110,10 @@ int launch_lstm_pp(Batch* b, const sttlstm::LstmParams& lp, int grid, cudaStream
   if (mode == 1) return launch_lstm_pp_inst<1, 12>(b, lp, grid, st);
   if (mode == 8) {   // four pairs per cluster share the h tiles by TMA multicast; falls back when 8-CTA clusters do not fit
     const int rc = launch_lstm_pp_inst<4, 3, 8>(b, lp, grid, st);
+    if (rc <= 0) return rc;
+  }
+  if (mode == 8 || mode == 5) {   // two pairs per cluster
+    const int rc = launch_lstm_pp_inst<4, 3, 4>(b, lp, grid, st);
     if (rc <= 0) return rc;
   }
   return launch_lstm_pp_inst<4, 3>(b, lp, grid, st);

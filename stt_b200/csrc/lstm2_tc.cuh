@@ -17,6 +17,7 @@
 
 namespace sttlstm {
 
+constexpr int kPPCounters = 32;   // grid-barrier counters (per group), 128 B apart, one per lane of the producer warp
 constexpr int kPairN = 128;        // gate columns per CTA pair
 constexpr int kPairCells = 32;
 constexpr int kPairStages = 8;
@@ -57,6 +58,15 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           ptx::smem_u32(bar)),
       "h"((uint16_t)3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0,
+                                                 int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          ptx::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 
@@ -277,7 +287,6 @@ lstm_pair_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
 //     moved at that rate), so small requests, not L2, were what bounded the kernels above at 30-45 B/clk per SM.
 constexpr int kPPEpiWarps = 16;
 constexpr int kPPThreads = 64 + kPPEpiWarps * 32;
-constexpr int kPPCounters = 32;  // grid-barrier counters per group, 128 B apart, one per lane of the producer warp
 template <int KB, int STAGES>
 struct PPSmem {
   static constexpr int kTile = 64 * BLOCK_K * 2;       // 64 rows of one K block: 8 KB
@@ -287,15 +296,6 @@ struct PPSmem {
   static constexpr int kBarrierOffset = STAGES * kStageBytes;
   static constexpr int kTotal = kBarrierOffset + 512 + 1024;
 };
-
-__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0,
-                                                 int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          ptx::smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 
 // The same load delivered to every CTA of `cta_mask` (same shared-memory offset in each); with cta_group::2 the bytes
 // are accounted on the mbarrier at this offset in the EVEN CTA of each destination's pair, which is why the barrier
@@ -320,7 +320,7 @@ constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the bit that tells th
 // tmap_h / tmap_wh: 3-D maps {64 columns, rows, K block} with box {64, 64, KB}.  Launch: cooperative, cluster (CS,1,1).
 // p.barrier: 2 groups x kPPCounters counters, 128 B apart, zero-initialised.
 //
-// CS = 8 (needs KB = 4; tmap_h then has box {64, 64, 1}): the kernel is bound by what L2 can deliver -- 128 CTAs x 1 MB
+// CS = 4 / 8 (needs KB = 4; tmap_h then has box {64, 64, KB * 2 / CS}): the kernel is bound by what L2 can deliver -- 128 CTAs x 1 MB
 // per step = 128 MB / 21.5 k cycles = 5.9 KB/clk, the measured ceiling of the L2 slices -- and half of that is the SAME h
 // rows fetched by all 64 pairs.  Four pairs share a cluster: each CTA fetches ONE of the four K blocks of its 64 rows
 // and multicasts it to the four CTAs of its parity, so a step reads h 16 times instead of 64 (80 MB instead of 128).
@@ -329,7 +329,8 @@ template <int KB, int STAGES, int CS = 2>
 __global__ void __launch_bounds__(kPPThreads, 1)
 lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_wh,
                const LstmParams p) {
-  static_assert(CS == 2 || (CS == 8 && KB == 4), "multicast variant: one K block per pair of the cluster");
+  static_assert(CS == 2 || ((CS == 4 || CS == 8) && KB == 4), "multicast variant: KB * 2 / CS K blocks per CTA");
+  constexpr int kSlice = KB * 2 / CS;   // K blocks of the h tile this CTA fetches for its parity (multicast variant)
   using L = PPSmem<KB, STAGES>;
   constexpr int kPPStages = STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -412,8 +413,9 @@ lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
               tma_load_3d_pair(sa, &tmap_h, leader_full, 0, row0, kb * KB);
             } else {
               // this CTA's K block of the 64 rows, for the four CTAs of its parity in the cluster
-              tma_load_3d_pair_mcast(sa + qpair * L::kTile, &tmap_h, leader_full, 0, row0, kb * KB + (int)qpair,
-                                     crank ? (uint16_t)0xAA : (uint16_t)0x55);
+              constexpr uint16_t kEven = (uint16_t)(0x55u & ((1u << CS) - 1u));
+              tma_load_3d_pair_mcast(sa + qpair * kSlice * L::kTile, &tmap_h, leader_full, 0, row0, kb * KB + (int)qpair * kSlice,
+                                     crank ? (uint16_t)(kEven << 1) : kEven);
             }
             if (++stage == kPPStages) { stage = 0; phase ^= 1; }
           }
@@ -457,7 +459,7 @@ lstm_pp_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_constant
                 umma_commit_pair(&empty_bar[stage]);
                 if (kb == num_k_blocks - 1) umma_commit_pair(&tmem_full_bar[g]);
               } else {
-                umma_commit_pair_mask(&empty_bar[stage], (uint16_t)0xFF);          // every CTA's producer counts this pair
+                umma_commit_pair_mask(&empty_bar[stage], (uint16_t)((1u << CS) - 1u));   // every CTA's producer counts this pair
                 if (kb == num_k_blocks - 1) umma_commit_pair_mask(&tmem_full_bar[g], (uint16_t)(3u << (2 * qpair)));
               }
             }
