@@ -42,8 +42,7 @@ constexpr int kMaxClasses = 64;
 constexpr int kMaxWordBytes = 128;
 constexpr int kStateWords = sttscorer::kMaxOrder - 1;
 constexpr int kMaxHotWords = 32;
-constexpr int kCommitRounds = 8;   // candidate rounds (of NT) compacted per scan in phase 6
-constexpr int kSelBins = 2048;     // phase 5: bins of the one-pass score histogram
+constexpr int kCommitSpan = 4096;  // candidates compacted per scan in phase 6 (4096 / NT rounds of NT)
 constexpr int kSelBoundaryCap = 256;  // phase 5: boundary-bin elements resolved by pairwise ranking (more: radix passes)
 // "not computed" marker of Slot::lm_cond (a quiet NaN no LM result can equal)
 constexpr unsigned long long kLmUnset = 0x7ff8dead5117b200ull;
@@ -632,9 +631,13 @@ template <int NT, int WC, int NC, bool kInstr>
 #ifndef STT_DEC_MINBLOCKS   // A/B builds only (Makefile `variant`)
 #define STT_DEC_MINBLOCKS 2
 #endif
+// Measured alternatives (round 2, B200): 256 threads with two prefixes each (128 registers, no spills) 9.3 ms vs 8.8;
+// one CTA per SM with 128 registers 6.35 ms alone but two waves for 256 utterances; 384 threads neutral (round 1).
 __global__ void __launch_bounds__(NT, (WC <= 512 ? STT_DEC_MINBLOCKS : 1))
 decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
-  static_assert(NT == 512, "phase 6 assumes 16 warps (kCommitRounds * 16 warp counts scanned by one warp)");
+  static_assert(NT == 512 || NT == 256, "phase 6: 128 (round, warp) counts, four per lane of the scanning warps");
+  constexpr int kCommitRounds = kCommitSpan / NT;   // candidate rounds (of NT) compacted per scan in phase 6
+  constexpr int kSelBins = 4 * NT;                  // phase 5: bins of the one-pass score histogram (one uint4 per thread)
   __shared__ Slot s_slot;   // the slot's pointers and capacities are read all over the step loop
   const int tid = threadIdx.x;
   if (tid < (int)(sizeof(Slot) / 4)) reinterpret_cast<uint32_t*>(&s_slot)[tid] = reinterpret_cast<const uint32_t*>(&slots[blockIdx.x])[tid];
@@ -1217,7 +1220,7 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
       main_sync<NT>();
       uint32_t round_off[kCommitRounds], round_total;
       {
-        // entry (q, w) sits at index q * 16 + w; lane l holds entries 4l .. 4l+3, i.e. round l / 4, warps 4 (l % 4) .. +3
+        // entry (q, w) sits at index q * (NT / 32) + w; lane l holds entries 4l .. 4l+3
         constexpr int PER = kCommitRounds * (NT / 32) / 32;  // entries per lane
         static_assert(PER == 4, "lane <-> (round, warp) mapping below");
         const uint4 v4 = reinterpret_cast<const uint4*>(s_cnt)[lane];
@@ -1231,7 +1234,7 @@ decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) 
         const int sub = warp & 3;
         const uint32_t pre = (incl - sum) + (sub > 0 ? v4.x : 0u) + (sub > 1 ? v4.y : 0u) + (sub > 2 ? v4.z : 0u);
 #pragma unroll
-        for (int q = 0; q < kCommitRounds; ++q) round_off[q] = __shfl_sync(0xffffffffu, pre, q * 4 + (warp >> 2));
+        for (int q = 0; q < kCommitRounds; ++q) round_off[q] = __shfl_sync(0xffffffffu, pre, (q * (NT / 32) + warp) >> 2);
         round_total = __shfl_sync(0xffffffffu, incl, 31);
       }
 #pragma unroll
