@@ -196,10 +196,16 @@ STT_EXPORT int STTX_BatchCopyProbs(STTX_Batch* b, unsigned int u, float* out);  
 STT_EXPORT int STTX_BatchSetProbs(STTX_Batch* b, const float* probs, const int* T, unsigned int n, unsigned int T_stride);
 /* decoder-only entry (the reference's Python ctc_beam_search_decoder_batch takes f64 probabilities) */
 STT_EXPORT int STTX_BatchSetProbs64(STTX_Batch* b, const double* probs, const int* T, unsigned int n, unsigned int T_stride);
-/* bring-up: TMEM layout of a CTA-pair MMA (M = 128 or 256); out = float[2][128][128] */
+/* Unit-test / bring-up hooks.  NOT part of the product library: they exist only in stt_b200/libstt_b200_dev.so, the same
+ * sources compiled with -DSTT_B200_DEV_HOOKS (tests/test_gpu_gemm.py, tests/native/probe_pair.py). */
+#ifdef STT_B200_DEV_HOOKS
+/* TMEM layout of a CTA-pair MMA (M = 128 or 256); out = float[2][128][128] */
 STT_EXPORT int STTX_DebugPairLayout(int M, float* out);
+/* one GEMM of the acoustic model's kernels on caller data; epilogue: 0 clipped-ReLU fp16, 1 bias f32, 2 softmax (N = 32 or
+ * 256), + 16 = the one-CTA kernel instead of the CTA-pair kernel */
 STT_EXPORT int STTX_DebugGemm(int M, int N, int K, const unsigned short* a_f16, const unsigned short* w_f16,
                               const float* bias, int epilogue, float relu_clip, void* out, float* ms);
+#endif
 /* how many times this stream's device context has garbage-collected its decoder arena (streams are unbounded in length;
  * PathTrie::remove, path_trie.cpp:192-209, is what bounds the reference's memory) */
 STT_EXPORT long long STTX_StreamArenaCompactions(const StreamingState* aSctx);

@@ -56,8 +56,27 @@ DECLARED_SYMBOLS = [
     "STTX_SpeechToTextBatch", "STTX_BatchCreate", "STTX_BatchFree", "STTX_BatchUpload", "STTX_BatchForward",
     "STTX_BatchDecode", "STTX_BatchNumResults", "STTX_BatchTranscript", "STTX_BatchTokens", "STTX_BatchFetch",
     "STTX_BatchGetTimings", "STTX_BatchKernelLaunches", "STTX_BatchSetInstrumented", "STTX_BatchTimesteps", "STTX_BatchCopyFeatures",
-    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_DebugGemm", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchDecoderScalars", "STTX_BatchSetCutoff", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_DebugPairLayout", "STTX_InspectModel", "STTX_InspectModelTensor", "STTX_StreamArenaCompactions",
+    "STTX_BatchCopyProbs", "STTX_BatchSetProbs", "STTX_ModelInfo", "STTX_BatchLmStats", "STTX_BatchDecoderScalars", "STTX_BatchSetCutoff", "STTX_BatchPhaseCycles", "STTX_BatchHostBuffer", "STTX_BatchLstmProfile", "STTX_BatchSetProbs64", "STTX_InspectModel", "STTX_InspectModelTensor", "STTX_StreamArenaCompactions",
 ]
+
+
+_dev = None
+
+
+def dev_lib():
+    """The unit-test build of the same sources (libstt_b200_dev.so = + STTX_DebugGemm / STTX_DebugPairLayout).  Test
+    infrastructure: nothing in this package calls it."""
+    global _dev
+    if _dev is None:
+        p = os.path.join(_HERE, "libstt_b200_dev.so")
+        if not os.path.exists(p):
+            raise STTError("%s is missing: run `make`" % p)
+        L = ctypes.CDLL(p)
+        L.STTX_DebugPairLayout.argtypes = [c_int, c_void_p]
+        L.STTX_DebugGemm.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                                     POINTER(c_float)]
+        _dev = L
+    return _dev
 
 
 def lib():
@@ -143,9 +162,6 @@ def lib():
     L.STTX_BatchCopyProbs.argtypes = [vp, c_uint, c_void_p]
     L.STTX_BatchSetProbs.argtypes = [vp, c_void_p, c_void_p, c_uint, c_uint]
     L.STTX_BatchSetProbs64.argtypes = [vp, c_void_p, c_void_p, c_uint, c_uint]
-    L.STTX_DebugPairLayout.argtypes = [c_int, c_void_p]
-    L.STTX_DebugGemm.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
-                                 POINTER(c_float)]
     L.STTX_ModelInfo.argtypes = [vp] + [POINTER(c_uint)] * 5
     _lib = L
     return L

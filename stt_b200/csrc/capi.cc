@@ -623,11 +623,13 @@ int STTX_BatchSetProbs(STTX_Batch* b, const float* probs, const int* T, unsigned
 int STTX_BatchSetProbs64(STTX_Batch* b, const double* probs, const int* T, unsigned int n, unsigned int T_stride) {
   return stteng::batch_set_probs64(b->dev, probs, T, (int)n, (int)T_stride) ? STT_ERR_FAIL_RUN_SESS : STT_ERR_OK;
 }
+#ifdef STT_B200_DEV_HOOKS
 int STTX_DebugPairLayout(int M, float* out) { return stteng::debug_pair_layout(M, out); }
 int STTX_DebugGemm(int M, int N, int K, const unsigned short* a_f16, const unsigned short* w_f16, const float* bias,
                    int epilogue, float relu_clip, void* out, float* ms) {
   return stteng::debug_gemm(M, N, K, a_f16, w_f16, bias, epilogue, relu_clip, out, ms);
 }
+#endif
 int STTX_ModelInfo(const ModelState* aCtx, unsigned int* n_classes, unsigned int* n_input, unsigned int* n_hidden,
                    unsigned int* n_steps, unsigned int* n_sms) {
   const sttmodel::HostModel& m = stteng::engine_model(aCtx->engine);

@@ -22,7 +22,9 @@
 #include "gemm_tc.cuh"
 #include "gemm2_tc.cuh"
 #include "lstm2_tc.cuh"
+#ifdef STT_B200_DEV_HOOKS
 #include "probe_tc.cuh"
+#endif
 #include "lstm_tc.cuh"
 #include "mfcc.cuh"
 #include "scorer_image.h"
@@ -1875,30 +1877,36 @@ int batch_stream_last_probs(Batch* b, std::vector<double>* out, int* n_rows) {
   return 0;
 }
 
+#ifdef STT_B200_DEV_HOOKS   // unit-test / bring-up entry points: built into libstt_b200_dev.so only (Makefile)
 // ====================================================================================== GEMM unit-test hook
 int debug_gemm(int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16, const float* bias, int epi,
                float relu_clip, void* out, float* ms) {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int BN = (epi == sttgemm::kEpiSoftmaxF32) ? 32 : 256;
+  // epi: 0 clipped-ReLU -> fp16, 1 bias -> f32, 2 softmax -> probs (N = 32: 29 classes; N = 256: 200 classes, the wide
+  // epilogue); + 16 selects the one-CTA 128 x 256 kernel instead of the CTA-pair 256 x 256 kernel for epilogues 0 / 1
+  const bool single = (epi & 16) != 0;
+  epi &= 15;
+  const int BN = (epi == sttgemm::kEpiSoftmaxF32) ? (N == 256 ? 256 : 32) : 256;
   if (N % BN != 0 || K % 8 != 0) return -2;
   __half *dA, *dW;
   float* dB;
   void* dO;
   const size_t out_elem = (epi == sttgemm::kEpiClipReluF16) ? 2 : 4;
-  const int n_valid = (epi == sttgemm::kEpiSoftmaxF32) ? std::min(N, 29) : N;
+  const int n_valid = (epi == sttgemm::kEpiSoftmaxF32) ? (N == 256 ? 200 : std::min(N, 29)) : N;
   const size_t out_count = (epi == sttgemm::kEpiSoftmaxF32) ? (size_t)M * n_valid : (size_t)M * N;
-  CUDA_OK(cudaMalloc((void**)&dA, (size_t)(M + 128) * K * 2));
+  CUDA_OK(cudaMalloc((void**)&dA, (size_t)(M + 256) * K * 2));
   CUDA_OK(cudaMalloc((void**)&dW, (size_t)N * K * 2));
   CUDA_OK(cudaMalloc((void**)&dB, (size_t)N * 4));
   CUDA_OK(cudaMalloc(&dO, out_count * out_elem));
-  CUDA_OK(cudaMemset(dA, 0, (size_t)(M + 128) * K * 2));
+  CUDA_OK(cudaMemset(dA, 0, (size_t)(M + 256) * K * 2));
   CUDA_OK(cudaMemcpy(dA, a_f16, (size_t)M * K * 2, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(dW, w_f16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
   CUtensorMap ta, tb;
-  if (!make_tmap_2d(&ta, dA, M + 128, K, K, 128) || !make_tmap_2d(&tb, dW, N, K, K, BN)) return -1;
+  const bool pair = !single && epi != sttgemm::kEpiSoftmaxF32;
+  if (!make_tmap_2d(&ta, dA, M + 128, K, K, 128) || !make_tmap_2d(&tb, dW, N, K, K, pair ? 128 : BN)) return -1;
   sttgemm::GemmParams p{};
   p.M = M; p.N = N; p.K = round_up(K, 64); p.bias = dB; p.out = dO; p.relu_clip = relu_clip; p.n_valid = n_valid;
   p.B = 1; p.T = M; p.out_T_stride = M; p.out_t_offset = 0;
@@ -1909,8 +1917,11 @@ int debug_gemm(int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16
   std::atomic<uint32_t> mask{0};
   for (int it = 0; it < 2 && rc == 0; ++it) {  // second run is the timed one
     cudaEventRecord(e0, 0);
-    if (epi == sttgemm::kEpiClipReluF16) rc = launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
-    else if (epi == sttgemm::kEpiBiasF32) rc = launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
+    if (epi == sttgemm::kEpiClipReluF16) rc = pair ? launch_gemm2<sttgemm::kEpiClipReluF16>(ta, tb, p, sms, 0, &mask)
+                                                  : launch_gemm<256, sttgemm::kEpiClipReluF16, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
+    else if (epi == sttgemm::kEpiBiasF32) rc = pair ? launch_gemm2<sttgemm::kEpiBiasF32>(ta, tb, p, sms, 0, &mask)
+                                                    : launch_gemm<256, sttgemm::kEpiBiasF32, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
+    else if (BN == 256) rc = launch_gemm<256, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
     else rc = launch_gemm<32, sttgemm::kEpiSoftmaxF32, sttgemm::kRows2D>(ta, tb, p, sms, 0, &mask);
     cudaEventRecord(e1, 0);
     if (cudaDeviceSynchronize() != cudaSuccess) rc = -1;
@@ -1956,5 +1967,7 @@ int debug_pair_layout(int M, float* out) {
   cudaFree(dA); cudaFree(dB); cudaFree(dO);
   return 0;
 }
+
+#endif  // STT_B200_DEV_HOOKS
 
 }  // namespace stteng

@@ -71,8 +71,10 @@ long long batch_stream_compactions(const Batch* b);                         // a
 int batch_stream_last_probs(Batch* b, std::vector<double>* out, int* n_rows);
 
 // raw GEMM hook for the kernel unit tests: C = epi(A[M,K] * W[N,K]^T + bias)
+#ifdef STT_B200_DEV_HOOKS
 int debug_pair_layout(int M, float* out);
 int debug_gemm(int M, int N, int K, const uint16_t* a_f16, const uint16_t* w_f16, const float* bias, int epi,
                float relu_clip, void* out, float* ms);
+#endif
 
 }  // namespace stteng

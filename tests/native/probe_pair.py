@@ -6,7 +6,7 @@ from stt_b200 import api
 
 for M in (256, 128):
     out = np.zeros((2, 128, 128), np.float32)
-    rc = api.lib().STTX_DebugPairLayout(M, out.ctypes.data)
+    rc = api.dev_lib().STTX_DebugPairLayout(M, out.ctypes.data)
     print("M=%d rc=%d" % (M, rc))
     v = out.astype(np.int64)
     row = v // 1024 - 1

@@ -10,8 +10,14 @@ import pytest
 from conftest import ROOT, _have_gpu
 
 
-def _declared():
+def _declared(dev_hooks=False):
     hdr = open(os.path.join(ROOT, "include", "stt_capi.h")).read()
+    hooks = re.findall(r"#ifdef STT_B200_DEV_HOOKS(.*?)#endif", hdr, flags=re.S)
+    if dev_hooks:
+        hdr = "\n".join(hooks)
+    else:
+        for h in hooks:   # declared for the unit-test build only (libstt_b200_dev.so)
+            hdr = hdr.replace(h, "")
     return sorted(set(re.findall(r"STT_EXPORT[^;(]*?\b(STTX?_[A-Za-z0-9]+)\s*\(", hdr)))
 
 
@@ -28,6 +34,11 @@ def test_library_exports_every_declared_symbol():
     exported = subprocess.run(["nm", "-D", "--defined-only", api.lib_path()], capture_output=True, text=True).stdout
     other = [l.split()[-1] for l in exported.splitlines() if " T " in l and not l.split()[-1].startswith(("STT_", "STTX_"))]
     assert other == [], "only the C ABI may be exported: %s" % other[:5]
+    # the unit-test hooks live in the dev build only
+    hooks = _declared(dev_hooks=True)
+    assert hooks and not any(hasattr(L, n) for n in hooks), "test hooks must not be exported by the product library"
+    dev = ctypes.CDLL(os.path.join(os.path.dirname(api.lib_path()), "libstt_b200_dev.so"))
+    assert all(hasattr(dev, n) for n in hooks + names)
 
 
 def test_struct_layout_matches_reference_abi():
