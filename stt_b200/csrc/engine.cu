@@ -626,7 +626,8 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
     return sttscorer::SCORER_UNREADABLE;
   }
   ds->blob_bytes = n;
-  const size_t vocab_end = std::min<size_t>(n, (size_t)(v.vocab_off + v.vocab_count * 8 + 16));
+  const size_t vocab_end = std::min<size_t>(n, (size_t)(v.probing ? v.pvocab_off + v.pvocab_buckets * 12 + 16
+                                                                  : v.vocab_off + v.vocab_count * 8 + 16));
   ds->vocab_host.assign(bytes, bytes + vocab_end);
   ds->vocab_host.resize(vocab_end + 16, 0);
   v.blob = ds->blob;

@@ -95,14 +95,52 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
   memcpy(&search_version, file + pos + 16, 4);
   pos += 20;
   if (order < 2 || order > kMaxOrder) return SCORER_INVALID_LM;
-  if (model_type < 2 || model_type > 5) return SCORER_INVALID_LM;  // probing models: not produced by generate_lm.py
-  if (search_version != 1) return SCORER_INVALID_LM;                // TrieSearch::kVersion
+  if (model_type < 0 || model_type > 5 || model_type == 1) return SCORER_INVALID_LM;   // REST_PROBING: no fixture to verify against
+  const bool probing = model_type == 0;                              // PROBING (model_type.hh:8-20)
+  if (search_version != (probing ? 0u : 1u)) return SCORER_INVALID_LM;   // HashedSearch::kVersion 0, TrieSearch::kVersion 1
+  float probing_multiplier;
+  memcpy(&probing_multiplier, file + kSanity + 4, 4);
   std::vector<uint64_t> counts(order);
   if (pos + 8ull * order > size) return SCORER_INVALID_LM;
   memcpy(counts.data(), file + pos, 8ull * order);
   const uint64_t header_size = ((kSanity + 20 + 8ull * order - 1) / 8 + 1) * 8;  // ALIGN8
 
   v->order = order;
+  uint64_t trie_offset = 0;
+  if (probing) {
+    // ---- probing-hash model (search_hashed.cc:206-220, vocab.cc:270-283): [vocabulary header 8 B + table of 12-byte
+    //      entries][unigram weights x (count + 1)][middle tables, 8 + weights bytes per entry][longest table, 12 bytes]
+    //      every table holds max(entries + 1, multiplier * entries) buckets (probing_hash_table.hh:108-111)
+    if (!(probing_multiplier >= 1.0f)) return SCORER_INVALID_LM;
+    auto buckets_for = [&](uint64_t entries) {
+      const uint64_t scaled = (uint64_t)(probing_multiplier * (float)entries);
+      return std::max<uint64_t>(entries + 1, scaled);
+    };
+    v->probing = model_type == 0 ? 1 : 2;
+    v->weights_size = model_type == 0 ? 8 : 12;
+    uint64_t p = header_size;
+    v->pvocab_buckets = buckets_for(counts[0]);
+    v->pvocab_off = p + 8;
+    p += 8 + v->pvocab_buckets * 12;
+    v->vocab_off = v->pvocab_off;      // start of the vocabulary section (hot-word lookups keep a host copy up to here)
+    v->vocab_count = counts[0];        // word ids are < counts[0]
+    v->unigram_off = p;
+    p += (counts[0] + 1) * v->weights_size;
+    for (int i = 2; i < order; ++i) {
+      v->ptab_off[i - 2] = p;
+      v->ptab_buckets[i - 2] = buckets_for(counts[i - 1]);
+      p += v->ptab_buckets[i - 2] * (8 + v->weights_size);
+    }
+    v->ptab_off[order - 2] = p;
+    v->ptab_buckets[order - 2] = buckets_for(counts[order - 1]);
+    p += v->ptab_buckets[order - 2] * 12;
+    trie_offset = p;
+    if (size <= trie_offset) return SCORER_NO_TRIE;
+    v->blob = file;
+    v->bos_word = vocab_index(*v, reinterpret_cast<const uint8_t*>("<s>"), 3);
+    v->eos_word = vocab_index(*v, reinterpret_cast<const uint8_t*>("</s>"), 4);
+    v->bos_backoff = load_f32(file + v->unigram_off + (uint64_t)v->bos_word * v->weights_size + 4);
+  } else {
   v->quantized = (model_type - 2) & 1;
   v->bhiksha = ((model_type - 2) >> 1) & 1;
 
@@ -183,7 +221,7 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
   v->longest.word_mask = word_mask;
   v->longest.total_bits = word_bits + longest_quant_bits;
   p += ((1 + counts[order - 1]) * v->longest.total_bits + 7) / 8 + 8;
-  const uint64_t trie_offset = p;  // GetEndOfSearchOffset(), model.cc:265-267
+  trie_offset = p;  // GetEndOfSearchOffset(), model.cc:265-267
   if (size <= trie_offset) return SCORER_NO_TRIE;
 
   // <s>, </s>, begin-sentence backoff (model.cc:78-84)
@@ -196,6 +234,7 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
     unigram_find(*v, v->bos_word, ignored, prob, bo);
     v->bos_backoff = bo;
   }
+  }  // trie model
 
   // ---- 'TRIE' header (scorer.cpp:182-211)
   pos = trie_offset;

@@ -76,6 +76,12 @@ struct ScorerView {
   LongestView longest;
   uint32_t bos_word, eos_word;
   float bos_backoff;  // begin_sentence.backoff[0], model.cc:84
+  // --- probing-hash models (model_type PROBING / REST_PROBING, kenlm/lm/search_hashed.hh): 0 = trie model
+  uint32_t probing;          // 1 PROBING (ProbBackoff weights, 8 B), 2 REST_PROBING (RestWeights, 12 B)
+  uint32_t weights_size;
+  uint64_t pvocab_off, pvocab_buckets;           // ProbingVocabulary table: {u64 hash, u32 id} entries of 12 B
+  uint64_t ptab_off[kMaxOrder - 1];              // [0 .. order-3] middle tables {u64 key, weights}; [order-2] longest {u64 key, f32}
+  uint64_t ptab_buckets[kMaxOrder - 1];
   // --- 'TRIE' header
   uint32_t is_utf8;
   double alpha, beta;  // f32-rounded values held in f64 (scorer.cpp:346-351)
@@ -151,6 +157,17 @@ STT_HD uint64_t murmur64a(const uint8_t* key, uint32_t len, uint64_t seed) {
 
 // SortedVocabulary::Index: exact search of the 64-bit hash; any exact search returns the same slot.
 STT_HD uint32_t vocab_index_from_hash(const ScorerView& v, uint64_t hash) {
+  if (v.probing) {
+    // ProbingVocabulary::Index (vocab.hh:162-165): linear probing from hash % buckets, key 0 = empty (probing_hash_table.hh)
+    const uint8_t* tab = v.blob + v.pvocab_off;
+    uint64_t i = hash % v.pvocab_buckets;
+    for (;;) {
+      const uint64_t k = load_u64(tab + i * 12);
+      if (k == hash) return load_u32(tab + i * 12 + 8);
+      if (k == 0) return 0;  // <unk>
+      if (++i == v.pvocab_buckets) i = 0;
+    }
+  }
   const uint8_t* tab = v.blob + v.vocab_off;
   uint64_t lo = 0, hi = v.vocab_count;
   while (lo < hi) {
@@ -286,8 +303,76 @@ STT_HD bool longest_find(const ScorerView& v, uint32_t word, const NodeRange& no
   return true;
 }
 
+// ------------------------------------------------------------------ probing-hash search (kenlm/lm/search_hashed.hh)
+STT_HD uint64_t combine_word_hash(uint64_t current, uint32_t next) {   // detail::CombineWordHash :26-29
+  return (current * 8978948897894561157ULL) ^ ((uint64_t)(1 + next) * 17894857484156487943ULL);
+}
+// ProbingHashTable::Find with IdentityHash / DivMod: entry address or null
+STT_HD const uint8_t* probing_find(const ScorerView& v, int table, uint32_t entry_size, uint64_t key) {
+  const uint8_t* tab = v.blob + v.ptab_off[table];
+  const uint64_t buckets = v.ptab_buckets[table];
+  uint64_t i = key % buckets;
+  for (;;) {
+    const uint64_t k = load_u64(tab + i * entry_size);
+    if (k == key) return tab + i * entry_size;
+    if (k == 0) return nullptr;
+    if (++i == buckets) i = 0;
+  }
+}
+// GenericModel<HashedSearch<...>>::FullScore: the same ResumeScore walk (model.cc:285-338) with the hashed lookups
+// (LookupUnigram / LookupMiddle / LookupLongest, search_hashed.hh:96-129); a stored probability's SIGN BIT says whether
+// the n-gram extends to the left (GenericProbingProxy, value.hh:15-38), its value is the number with the sign bit set.
+STT_HD float full_score_probing(const ScorerView& v, const LmState& in, uint32_t new_word, LmState& out) {
+  const uint8_t* u = v.blob + v.unigram_off + (uint64_t)new_word * v.weights_size;
+  const uint32_t pu = load_u32(u);
+  float prob = sttmath::as_f32(pu | 0x80000000u);
+  const float bo = load_f32(u + 4);
+  bool independent_left = (pu & 0x80000000u) != 0;
+  uint64_t node = (uint64_t)new_word;
+  uint8_t ngram_length = 1;
+  out.backoff[0] = bo;
+  out.length = has_extension(bo) ? 1 : 0;
+  out.words[0] = new_word;
+  if (in.length != 0) {
+    int order_minus_2 = 0;
+    int hist = 0;
+    float* backoff_out = out.backoff + 1;
+    bool broke = false;
+    const uint32_t mid_entry = 8 + v.weights_size;
+    for (;; ++order_minus_2, ++hist, ++backoff_out) {
+      if (hist == in.length) break;
+      if (independent_left) break;
+      if (order_minus_2 == (int)v.order - 2) {
+        broke = true;
+        break;
+      }
+      node = combine_word_hash(node, in.words[hist]);
+      const uint8_t* e = probing_find(v, order_minus_2, mid_entry, node);
+      if (!e) break;   // independent_left = true; not found
+      const uint32_t pm = load_u32(e + 8);
+      independent_left = (pm & 0x80000000u) != 0;
+      const float b = load_f32(e + 12);
+      *backoff_out = b;
+      prob = sttmath::as_f32(pm | 0x80000000u);
+      ngram_length = (uint8_t)(order_minus_2 + 2);
+      if (has_extension(b)) out.length = ngram_length;
+    }
+    if (broke) {
+      const uint8_t* e = probing_find(v, (int)v.order - 2, 12, combine_word_hash(node, in.words[hist]));
+      if (e) {
+        prob = load_f32(e + 8);
+        ngram_length = (uint8_t)v.order;
+      }
+    }
+    for (int i = 0; i + 1 < (int)out.length; ++i) out.words[i + 1] = in.words[i];
+  }
+  for (int i = ngram_length - 1; i < (int)in.length; ++i) prob += in.backoff[i];
+  return prob;
+}
+
 // GenericModel::FullScore (model.cc:170-176) = ScoreExceptBackoff + charged backoffs.
 STT_HD float full_score(const ScorerView& v, const LmState& in, uint32_t new_word, LmState& out) {
+  if (v.probing) return full_score_probing(v, in, new_word, out);
   NodeRange node;
   float prob, bo;
   unigram_find(v, new_word, node, prob, bo);

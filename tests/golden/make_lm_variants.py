@@ -7,6 +7,7 @@ the reference's own `build_binary` (oracle/_ref/build_binary) and packaged by th
   quant_trie.scorer        QUANT_TRIE        -q 8 -b 8
   array_trie.scorer        ARRAY_TRIE        -a 64      (Bhiksha-compressed next pointers)
   quant_array_trie.scorer  QUANT_ARRAY_TRIE  -q 8 -b 8 -a 255   (what released .scorer files use)
+  probing.scorer           PROBING           -p 1.5             (linear-probing hash tables, kenlm/lm/search_hashed.hh)
 (all with -v: no vocabulary strings after the search section, as data/lm/generate_lm.py builds them)
 """
 import os
@@ -43,10 +44,12 @@ spellable = [w for w in words if w and all(c in letters for c in w)]
 
 alpha = o.RefAlphabet(synth.ENGLISH_LABELS)
 variants = {"trie": [], "quant_trie": ["-q", "8", "-b", "8"], "array_trie": ["-a", "64"],
-            "quant_array_trie": ["-q", "8", "-b", "8", "-a", "255"]}
+            "quant_array_trie": ["-q", "8", "-b", "8", "-a", "255"],
+            "probing": ["-p", "1.5"]}          # model_type PROBING: hash tables instead of the trie (kenlm/lm/search_hashed.hh)
 for name, flags in variants.items():
     lm = os.path.join(OUT, name + ".binary")
-    subprocess.check_call([BUILD_BINARY] + flags + ["-v", "trie", ARPA, lm], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call([BUILD_BINARY] + flags + ["-v", "probing" if name == "probing" else "trie", ARPA, lm],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     pkg = os.path.join(OUT, name + ".scorer")
     rc = o.ref().ref_make_scorer_package(lm.encode(), b"".join(w.encode() + b"\0" for w in spellable), len(spellable),
                                          alpha.h, pkg.encode(), 0.9, 1.2)

@@ -194,7 +194,7 @@ def test_decoder_against_committed_golden(small_model):
         assert conf == float(g["confidence"][u])
 
 
-@pytest.mark.parametrize("layout", ["trie", "quant_trie", "array_trie", "quant_array_trie"])
+@pytest.mark.parametrize("layout", ["trie", "quant_trie", "array_trie", "quant_array_trie", "probing"])
 def test_decoder_with_every_kenlm_trie_layout(ref_decoder, small_model, english, layout):
     """Order-5 scorers in the four trie layouts (tests/golden/make_lm_variants.py, from kenlm's lm/test.arpa): the GPU
     decoder -- word ordinals, carried KenLM states, interpolation searches, Bhiksha next pointers -- against the

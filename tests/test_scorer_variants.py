@@ -1,4 +1,5 @@
-"""The four KenLM trie layouts a .scorer can carry (model_type TRIE / QUANT_TRIE / ARRAY_TRIE / QUANT_ARRAY_TRIE,
+"""The KenLM model types a .scorer can carry (the four trie layouts TRIE / QUANT_TRIE / ARRAY_TRIE / QUANT_ARRAY_TRIE and the
+probing-hash model PROBING,
 kenlm/lm/model_type.hh:8-20), order 5, built from kenlm's own lm/test.arpa by tests/golden/make_lm_variants.py:
 the scorer view (the code the CUDA decoder compiles, here compiled for the host) must equal the compiled reference
 (Scorer::get_log_cond_prob) bit for bit on every layout, and reproduce kenlm's model_test.cc known answers on the
@@ -12,7 +13,7 @@ import pytest
 
 from conftest import GOLDEN, ROOT
 
-VARIANTS = ["trie", "quant_trie", "array_trie", "quant_array_trie"]
+VARIANTS = ["trie", "quant_trie", "array_trie", "quant_array_trie", "probing"]
 LN10_F32 = float(np.float32(0.4342944819))  # NUM_FLT_LOGE, decoder_utils.h:13
 
 
@@ -77,7 +78,7 @@ def test_variant_matches_reference_bit_for_bit(checker, ref_decoder, english, na
         assert _score(S, h, ws, bos) == sc.log_cond_prob(ws, bos), (name, ws, bos)
 
 
-@pytest.mark.parametrize("name", ["trie", "array_trie"])
+@pytest.mark.parametrize("name", ["trie", "array_trie", "probing"])
 def test_kenlm_known_answers_on_unquantised_layouts(checker, english, name):
     """kenlm/lm/model_test.cc:69-101 (Starters / Continuation): FullScore along '<s> looking on a little' and
     'also would consider higher looking' -- log10 values, here through get_log_cond_prob's natural-log window."""
