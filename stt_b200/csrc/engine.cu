@@ -114,7 +114,7 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
 // Kernel attributes (opt-in shared memory) are per DEVICE: each Engine remembers which of its kernels it has configured
 // on its device in a bit mask.  Setting an attribute twice is harmless, so concurrent host threads need no lock.
 enum KernelBit {
-  kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitGemmSoftmaxWide, kBitDecGeneral, kBitGemm2Relu, kBitGemm2Bias, kBitGemm2Relu3, kBitGemm2Bias3, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
+  kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitGemmSoftmaxWide, kBitDecGeneral, kBitGemm2Relu, kBitGemm2Bias, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
   kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitLstmPP4Mc, kBitLstmPP4Mc4, kBitDec512, kBitDec512I, kBitDec2048, kBitDec2048I
 };
 template <class K>
@@ -150,20 +150,15 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::Gem
 }
 
 // CTA-pair 256 x 256 tiles (gemm2_tc.cuh) for the layers whose N is a multiple of 256; tb must have 128-row boxes.
-template <int EPI, int STAGES>
-int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, sttgemm::GemmParams p, int num_sms, cudaStream_t st,
-                      std::atomic<uint32_t>* cfg_mask, int chunk) {
+template <int EPI>
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::GemmParams& p, int num_sms, cudaStream_t st,
+                 std::atomic<uint32_t>* cfg_mask) {
+  constexpr int STAGES = 6;
   using L = sttgemm::Smem2Layout<STAGES>;
   auto kern = sttgemm::gemm2_tc_kernel<STAGES, EPI>;
-  const int bit = (EPI == sttgemm::kEpiClipReluF16 ? kBitGemm2Relu : kBitGemm2Bias) + (STAGES == 6 ? 0 : 2);
-  if (ensure_smem(cfg_mask, bit, kern, L::kTotal)) return -1;
+  if (ensure_smem(cfg_mask, EPI == sttgemm::kEpiClipReluF16 ? kBitGemm2Relu : kBitGemm2Bias, kern, L::kTotal)) return -1;
   const int n_tiles = ((p.M + 255) / 256) * (p.N / 256);
-  int pairs = std::max(1, std::min(n_tiles, num_sms / 2));
-  p.chunk = 0;
-  if (chunk > 0 && n_tiles > pairs) {
-    p.chunk = chunk;
-    pairs = (n_tiles + chunk - 1) / chunk;
-  }
+  const int pairs = std::max(1, std::min(n_tiles, num_sms / 2));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(sttgemm::kNumThreads);
@@ -176,13 +171,6 @@ int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, sttgemm::Gem
   cfg.numAttrs = 1;
   CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return 0;
-}
-int g_gemm2_stages = 6, g_gemm2_chunk = 0;   // measurement knobs, set once by engine_create
-template <int EPI>
-int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const sttgemm::GemmParams& p, int num_sms, cudaStream_t st,
-                 std::atomic<uint32_t>* cfg_mask) {
-  if (g_gemm2_stages == 3) return launch_gemm2_inst<EPI, 3>(ta, tb, p, num_sms, st, cfg_mask, g_gemm2_chunk);
-  return launch_gemm2_inst<EPI, 6>(ta, tb, p, num_sms, st, cfg_mask, g_gemm2_chunk);
 }
 
 }  // namespace
@@ -407,8 +395,6 @@ Engine* engine_create(const sttmodel::HostModel& m, std::string* err) {
     e->opt_dec_flags = geti("STT_B200_DEC_FLAGS", e->opt_dec_flags);
     e->opt_lstm_exact_h = geti("STT_B200_LSTM_EXACT_H", 1);
     e->opt_gemm_pair = geti("STT_B200_GEMM_PAIR", 1);
-    g_gemm2_stages = geti("STT_B200_GEMM2_STAGES", 6);
-    g_gemm2_chunk = geti("STT_B200_GEMM2_CHUNK", 0);
     e->verbose = getenv("STT_B200_VERBOSE") != nullptr;
     // A CUDA injection library (Nsight Compute / Systems) serialises kernels and, with this driver, fails launches that
     // carry BOTH the cooperative and the cluster attribute; see launch_lstm_*.

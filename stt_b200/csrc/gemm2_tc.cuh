@@ -83,12 +83,6 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int n_tiles = n_tiles_m * n_tiles_n;
   const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
   constexpr uint32_t kTmemCols = 512;
-  // Tile assignment: persistent striding over the grid (chunk == 0), or `chunk` consecutive tiles per pair with one pair
-  // per chunk in the grid -- then the hardware's block scheduler balances the load, and pairs of this GEMM start wherever
-  // SMs have room while another stream's kernel (the previous batch's decoder) still occupies the rest.
-  const int tile_begin = p.chunk > 0 ? pair_idx * p.chunk : pair_idx;
-  const int tile_end = p.chunk > 0 ? min(n_tiles, tile_begin + p.chunk) : n_tiles;
-  const int tile_step = p.chunk > 0 ? 1 : n_pairs;
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -120,7 +114,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      for (int tile = pair_idx; tile < n_tiles; tile += n_pairs) {
         const int m_blk = tile / n_tiles_n, n_blk = tile % n_tiles_n;
         const int a_row = m_blk * 2 * BLOCK_M + (int)crank * BLOCK_M;
         const int b_row = n_blk * BLOCK_N + (int)crank * 128;
@@ -143,7 +137,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      for (int tile = pair_idx; tile < n_tiles; tile += n_pairs) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -172,7 +166,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int row_in_cta = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+    for (int tile = pair_idx; tile < n_tiles; tile += n_pairs) {
       const int m_blk = tile / n_tiles_n, n_blk = tile % n_tiles_n;
       const int out_row = m_blk * 2 * BLOCK_M + (int)crank * BLOCK_M + row_in_cta;
       const bool valid = out_row < p.M;

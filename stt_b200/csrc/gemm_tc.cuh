@@ -43,7 +43,6 @@ struct GemmParams {
   int b_box, t_box;      // tile = t_box timesteps x b_box utterances, t_box * b_box == BLOCK_M
   // softmax output layout: probs[(b * T_stride + t_offset + t) * n_valid + c]
   int out_T_stride, out_t_offset;
-  int chunk;             // CTA-pair kernel: tiles per pair (0 = persistent striding over the grid)
 };
 
 template <int BLOCK_N, int STAGES>
