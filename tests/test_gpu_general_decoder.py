@@ -275,3 +275,41 @@ def test_hot_words_in_the_general_kernel(ref_decoder, vocab_words, english):
         ref = _ref_decode_hot(o, probs[u], T, ra, rs, 100, hot, 2, 0.995, 12)
         for g, r in zip(got[u], ref):
             assert _same(g, r), ("pruned hot words", u, g, r)
+
+
+def test_thirty_two_labels_use_the_shared_memory_decoder_and_the_wide_softmax(oracle, ref_decoder):
+    """33 classes: the largest alphabet the label-mask kernel takes (32 labels), one class more than the 32-column softmax
+    tile holds -- the acoustic model's output layer runs the 256-column epilogue, the decoder the shared-memory kernel."""
+    from stt_b200 import Model, synth
+    o = ref_decoder
+    labels = [" "] + [chr(ord("a") + i) for i in range(26)] + ["'", "-", ".", ",", "?"]
+    assert len(labels) == 32
+    w = synth.make_weights(n_hidden=64, n_classes=33, seed=9)
+    w = synth.make_ctc_like(w, synth.np_mfcc(synth.make_pcm(32000, utt=777)), scale=200.0, blank_bias=6.0)
+    m = Model(synth.model_bytes(w, labels=labels, beam_width=64))
+    pcm = synth.make_pcm(48000, utt=5)
+    b = m.createBatch(1, pcm.size)
+    b.upload([pcm])
+    b.forward()
+    probs = b.probs(0)
+    assert probs.shape[1] == 33
+    ref_p, _ = oracle.PortAM(w).stream(pcm)
+    assert float(np.abs(probs - ref_p).max()) <= 4e-2   # x200 output layer vs fp32: tests/test_gpu_headline.py PROBS_ATOL_VS_FP32
+    ra = o.RefAlphabet(labels)
+    md = m.sttWithMetadata(pcm, 3)
+    ref = o.ref_decode(probs, ra, 64, None, num_results=3)
+    assert len(md.transcripts) == len(ref) and len(ref[0][1]) > 5
+    for t, (rc, rt, rts) in zip(md.transcripts, ref):
+        assert "".join(x.text for x in t.tokens) == ra.decode(rt) and [x.timestep for x in t.tokens] == list(rts)
+        assert t.confidence == rc
+
+
+def test_general_kernel_wide_beam(ref_decoder):
+    """Beam 1500 over 256 classes with the multilingual bytes scorer: candidate arrays of 384 000 entries in global memory."""
+    o = ref_decoder
+    ra = o.RefByteAlphabet()
+    rs = o.RefScorer(BYTES_MULTI, ra)
+    m = _host_model(BYTE_LABELS, BYTES_MULTI, beam=1500)
+    rng = np.random.default_rng(31)
+    probs, lens = _batch(_byte_seqs(["señormüller", "東京タワー"]), 256, rng, noise=0.05)
+    _compare(o, m, ra, rs, probs, lens, 1500, 2, 1.0, 40, "bytes wide beam")
