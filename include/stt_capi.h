@@ -81,9 +81,10 @@ enum STT_Error_Codes {
 };
 
 /* ------------------------------------------------------------------------------------------------ PART 1 */
-/* coqui-stt.h:137-138 | stt.cc:374-379 (+ CreateModelImpl :336-372).  Accepts a `.sttw` model file. */
+/* coqui-stt.h:137-138 | stt.cc:374-379 (+ CreateModelImpl :336-372).  Accepts the reference's `.tflite` flatbuffer
+ * (native_client/tflitemodelstate.cc:161-338) or the native `.sttw` container. */
 STT_EXPORT int STT_CreateModel(const char* aModelPath, ModelState** retval);
-/* coqui-stt.h:150-152 | stt.cc:381-387.  The buffer is parsed and copied; it need not outlive the call. */
+/* coqui-stt.h:150-152 | stt.cc:381-387.  The buffer (either format) is parsed in place; it need not outlive the call. */
 STT_EXPORT int STT_CreateModelFromBuffer(const char* aModelBuffer, unsigned int aBufferSize, ModelState** retval);
 /* coqui-stt.h:164 | stt.cc:389-393 */
 STT_EXPORT unsigned int STT_GetModelBeamWidth(const ModelState* aCtx);

@@ -11,7 +11,9 @@ up to state numbering, and the decoder only ever asks "start state", "arc for la
 states breadth-first from the start (arcs sorted by label) yields a package the reference loads and decodes with
 identically -- tests/test_scorer_package.py checks exactly that against the compiled reference.
 
-Host-side tool, word mode only (bytes-output / UTF-8 mode is SURVEY 8f rank 4, not built).  Not on the hot path."""
+Word mode and bytes-output (UTF-8) mode (generate_scorer_package.cpp:27-50: inferred from the vocabulary -- all words one
+code point long -- unless forced; UTF-8 mode spells words in BYTES over the 255-label UTF8Alphabet and appends no space,
+decoder_utils.cpp:108-131).  Host-side tool, not on the hot path."""
 import struct
 
 KENLM_MAGIC = b"mmap lm http://kheafield.com/code format version 5\n\x00"
@@ -41,11 +43,12 @@ def _split_labels(word, label_to_id):
     return out
 
 
-def build_dictionary(words, labels):
-    """Minimal DFA over ilabels (= label + 1) accepting {spelling(w) + SPACE}.  Returns (start, final flags, arcs) with
-    arcs[state] = sorted list of (ilabel, next state), states numbered breadth-first from the start state 0."""
-    label_to_id = {l: i for i, l in enumerate(labels)}
-    space = label_to_id[" "] + 1
+def build_dictionary(words, labels, utf8=False):
+    """Minimal DFA over ilabels (= label + 1) accepting {spelling(w) + SPACE} -- or, in UTF-8 mode, {bytes(w)} over the
+    UTF8Alphabet (label = byte - 1, so ilabel = the byte).  Returns (start, final flags, arcs) with arcs[state] = sorted
+    list of (ilabel, next state), states numbered breadth-first from the start state 0."""
+    label_to_id = {l: i for i, l in enumerate(labels)} if not utf8 else {}
+    space = None if utf8 else label_to_id[" "] + 1
     # --- trie of the label paths
     children = [{}]
     final = [False]
@@ -53,12 +56,12 @@ def build_dictionary(words, labels):
     for w in sorted(set(words)):
         if w in ("<s>", "</s>", "<unk>") or not w:     # scorer.cpp:407
             continue
-        path = _split_labels(w, label_to_id)
-        if path is None:
+        path = [b for b in w.encode("utf-8")] if utf8 else _split_labels(w, label_to_id)
+        if path is None or (utf8 and 0 in path):
             continue
         n_words += 1
         s = 0
-        for lab in path + [space]:
+        for lab in (path if utf8 else path + [space]):
             nxt = children[s].get(lab)
             if nxt is None:
                 nxt = len(children)
@@ -136,19 +139,28 @@ def _const_fst_bytes(start, fin, arcs, offset):
     return bytes(out)
 
 
-def create_scorer_package(lm_path, vocab_words, labels, package_path, default_alpha, default_beta):
-    """generate_scorer_package --lm LM --vocab VOCAB --package OUT --default_alpha A --default_beta B (word mode).
-    `labels`: the model's alphabet in label order (must contain the space).  Returns (#words in the dictionary, #states,
-    #arcs).  The LM must be a KenLM trie binary built with -v (no vocabulary strings behind the search section)."""
+def looks_char_based(vocab_words):
+    """generate_scorer_package.cpp:29-40: every vocabulary word is one code point long."""
+    return all(len(w) <= 1 for w in vocab_words)
+
+
+def create_scorer_package(lm_path, vocab_words, labels, package_path, default_alpha, default_beta, utf8=None):
+    """generate_scorer_package --lm LM --vocab VOCAB --package OUT --default_alpha A --default_beta B
+    [--force_bytes_output_mode].  `labels`: the model's alphabet in label order (word mode: must contain the space; UTF-8
+    mode: ignored, the alphabet is the 255 byte values).  `utf8` None = inferred from the vocabulary like the reference.
+    Returns (#words in the dictionary, #states, #arcs).  The LM must be a KenLM binary built with -v (no vocabulary strings
+    behind the search section)."""
+    if utf8 is None:
+        utf8 = looks_char_based(vocab_words)
     lm = open(lm_path, "rb").read()
     if not lm.startswith(KENLM_MAGIC):
         raise ValueError("not a KenLM binary (format version 5): %s" % lm_path)
-    if " " not in labels:
-        raise ValueError("word-mode scorers need a space label in the alphabet")
+    if not utf8 and (labels is None or " " not in labels):
+        raise ValueError("word-mode scorers need an alphabet with a space label")
     if struct.pack("<i", TRIE_MAGIC) in lm[-(1 << 16):] and lm.rfind(struct.pack("<ii", TRIE_MAGIC, TRIE_FILE_VERSION)) >= 0:
         raise ValueError("the LM file already carries a 'TRIE' dictionary section: pass the bare KenLM binary")
-    start, fin, arcs, n_words = build_dictionary(vocab_words, labels)
-    head = struct.pack("<iiBdd", TRIE_MAGIC, TRIE_FILE_VERSION, 0, float(default_alpha), float(default_beta))
+    start, fin, arcs, n_words = build_dictionary(vocab_words, labels, utf8)
+    head = struct.pack("<iiBdd", TRIE_MAGIC, TRIE_FILE_VERSION, 1 if utf8 else 0, float(default_alpha), float(default_beta))
     fst = _const_fst_bytes(start, fin, arcs, len(lm) + len(head))
     with open(package_path, "wb") as f:
         f.write(lm)
@@ -175,17 +187,22 @@ def read_alphabet(path):
 
 def main(argv=None):
     import argparse
-    ap = argparse.ArgumentParser(description="Create a .scorer package (word mode) from a KenLM binary and a vocabulary.")
-    ap.add_argument("--alphabet", required=True, help="alphabet.txt: one label per line, '#' comments (alphabet.cc:42-68)")
+    ap = argparse.ArgumentParser(description="Create a .scorer package from a KenLM binary and a vocabulary.")
+    ap.add_argument("--alphabet", help="alphabet.txt: one label per line, '#' comments (alphabet.cc:42-68); word mode only")
+    ap.add_argument("--force_bytes_output_mode", type=int, choices=(0, 1), default=None,
+                    help="1 = UTF-8 bytes mode, 0 = word mode; default: inferred from the vocabulary like the reference")
     ap.add_argument("--lm", required=True)
     ap.add_argument("--vocab", required=True)
     ap.add_argument("--package", required=True)
     ap.add_argument("--default_alpha", type=float, required=True)
     ap.add_argument("--default_beta", type=float, required=True)
     a = ap.parse_args(argv)
-    labels = read_alphabet(a.alphabet)
     words = open(a.vocab, encoding="utf-8").read().split()
-    n, ns, na = create_scorer_package(a.lm, words, labels, a.package, a.default_alpha, a.default_beta)
+    utf8 = looks_char_based(words) if a.force_bytes_output_mode is None else bool(a.force_bytes_output_mode)
+    if not utf8 and not a.alphabet:
+        ap.error("word mode needs --alphabet (the reference asks for --checkpoint with an alphabet.txt)")
+    labels = read_alphabet(a.alphabet) if a.alphabet else None
+    n, ns, na = create_scorer_package(a.lm, words, labels, a.package, a.default_alpha, a.default_beta, utf8)
     print("%d words, %d states, %d arcs -> %s" % (n, ns, na, a.package))
     return 0
 

@@ -193,3 +193,39 @@ def test_dictionary_is_exact_and_minimal_on_random_vocabularies(english):
                     good.add(s)
                     changed = True
         assert len(good) == len(arcs)
+
+
+def test_bytes_output_mode_package_matches_the_reference(tmp_path, ref_decoder):
+    """UTF-8 mode (generate_scorer_package.cpp:27-50, decoder_utils.cpp:108-131): the vocabulary of code points of the
+    multilingual fixture, spelled in bytes without a trailing space; same automaton as the reference builds, accepted by
+    the reference loader as a UTF-8 scorer, identical reference decodes with either package."""
+    from stt_b200 import scorer_package as sp
+    o = ref_decoder
+    fixture = os.path.join(GOLDEN, "bytes", "multilingual.bytes.scorer")
+    lm = str(tmp_path / "lm.binary")
+    open(lm, "wb").write(_lm_bytes_of(fixture))
+    text = open(os.path.join(GOLDEN, "bytes", "multilingual.txt"), encoding="utf-8").read()
+    units = sorted({ch for ch in text if not ch.isspace()})
+    assert sp.looks_char_based(units) and not sp.looks_char_based(["ab"])
+    ours = str(tmp_path / "ours.scorer")
+    n, ns, na = sp.create_scorer_package(lm, units, None, ours, 0.9, 1.1)      # mode inferred: bytes
+    alpha = o.RefByteAlphabet()
+    theirs = str(tmp_path / "theirs.scorer")
+    rc = o.ref().ref_make_scorer_package_utf8(lm.encode(), b"".join(w.encode("utf-8") + b"\0" for w in units), len(units),
+                                              alpha.h, theirs.encode(), 0.9, 1.1)
+    assert rc == 0
+    ho, ht = _fst_header(ours), _fst_header(theirs)
+    assert ho[:4] == ht[:4] and ho[5:] == ht[5:] == (0, ns, na) and n == len(units)
+    assert os.path.getsize(ours) == os.path.getsize(theirs)
+    so, st = o.RefScorer(ours, alpha), o.RefScorer(theirs, alpha)
+    assert o.ref().ref_scorer_is_utf8(so.h) == 1
+    rng = np.random.default_rng(4)
+    T = 60
+    probs = rng.dirichlet(np.ones(256) * 0.05, size=T)
+    for t, b in enumerate("日本語caféß😀".encode("utf-8")):
+        probs[2 * t + 1, b - 1] += 3.0
+    probs /= probs.sum(1, keepdims=True)
+    ra, rb = o.ref_decode(probs, alpha, 64, so, num_results=3), o.ref_decode(probs, alpha, 64, st, num_results=3)
+    assert len(ra) == len(rb) > 0
+    for (ca, ta, tsa), (cb, tb, tsb) in zip(ra, rb):
+        assert ca == cb and list(ta) == list(tb) and list(tsa) == list(tsb)
