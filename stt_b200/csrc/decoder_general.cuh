@@ -116,6 +116,13 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
   int cur = 0;
   const bool use64 = in.probs64 != nullptr;
 
+#ifdef STT_GEN_PROF
+  unsigned long long gp_ph[7] = {0, 0, 0, 0, 0, 0, 0}, gp_n = 0;
+  long long gp_t = clock64();
+#define GEN_MARK(k) do { const long long _t = clock64(); gp_ph[k] += (unsigned long long)(_t - gp_t); gp_t = _t; } while (0)
+#else
+#define GEN_MARK(k) do { } while (0)
+#endif
   for (int step = 0; step < in.n_steps; ++step, ++abs_t) {
     float* const score = b_score[cur];
     float* const bprev = b_b[cur];
@@ -233,6 +240,7 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
       return (float)(cond * sv.alpha);
     };
 
+    GEN_MARK(0);   // row preparation, cutoff, parent slots
     // ---- updated values of the live prefixes (:150-256), events in the order the reference's loops produce them
     for (uint32_t j = tid; j < n_live; j += NT) {
       const float sj = score[j];
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
       utsp[j] = ts_prev;
     }
 
+    GEN_MARK(1);   // live update
     // ---- new children: count, scan, emit (two identical enumerations so that candidates land at deterministic offsets)
     uint32_t n_new = 0;
     for (int pass = 0; pass < 2; ++pass) {
@@ -323,7 +332,10 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
             if (p.has_scorer) c = (uint32_t)g.garc[a0 + a].x;
             if (c >= (uint32_t)blank || !s_ok[c]) continue;
             if (full_beam && s_logp[c] + si < min_cutoff) continue;
-            const uint32_t existing = ht_find_maybe(s, ni, c);
+            // Node::child_mask as a 32-bit filter over labels (bit = label mod 32, set when a child is created): nearly every
+            // (prefix, label) pair has never had a node, and the filter spares those the hash probe -- a dependent global
+            // round trip per arc, which is what this phase's time consisted of
+            const uint32_t existing = ((ndi.child_mask >> (c & 31u)) & 1u) ? ht_find_maybe(s, ni, c) : kNone;
             if (existing != kNone) {
               const uint32_t ls = s.nodes[existing].live_slot;
               if (ls < n_live && node[ls] == existing) continue;   // a live child pulls this extension itself
@@ -355,6 +367,7 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
       }
       if (!pass) n_new = run_base;
       __syncthreads();
+      if (!pass) GEN_MARK(6);   // the counting enumeration
       if (!pass && n_live + n_new > s.cand_cap) break;
     }
     const uint32_t N = n_live + n_new;
@@ -362,6 +375,10 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
     __threadfence_block();
     __syncthreads();
 
+    GEN_MARK(2);   // children
+#ifdef STT_GEN_PROF
+    gp_n += N;
+#endif
     // ---- exact top-W selection on the 64-bit key: radix passes, most significant byte first (:263-274)
     unsigned long long sel_prefix = 0, sel_mask = 0;
     if (N > (uint32_t)W) {
@@ -398,6 +415,7 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
       }
     }
 
+    GEN_MARK(3);   // select
     // ---- order-preserving compaction + commit (iterate_to_vec :159-190, remove :192-209)
     float* const nscore = b_score[cur ^ 1];
     float* const nbb = b_b[cur ^ 1];
@@ -445,6 +463,7 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
     }
     __threadfence_block();
     __syncthreads();
+    GEN_MARK(4);   // compaction
     // one thread per survivor: a new one gets its arena node (or is revived under its old identity), everybody stamps
     // Node::live_slot
     for (uint32_t pos = tid; pos < out_base; pos += NT) {
@@ -512,6 +531,7 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
           s.lm_meta[id] = meta_init;
           reinterpret_cast<unsigned long long*>(s.lm_cond)[id] = kLmUnset;
           ht_insert(s, pnode, c, id);
+          atomicOr(&s.nodes[pnode].child_mask, 1u << (c & 31u));
         }
       } else {
         s.nodes[id].live_slot = pos;
@@ -532,6 +552,7 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
     if (arena_count > s.arena_cap || ts_count > s.ts_cap) overflow = 1;
     n_live = out_base;
     cur ^= 1;
+    GEN_MARK(5);   // commit
   }
 
   // ---- leave the live list in the slot's own arrays
@@ -552,6 +573,11 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
     s.scalars[4] = abs_t;
     s.scalars[5] = start_expanding;
     s.scalars[6] = overflow;
+#ifdef STT_GEN_PROF
+    for (int q = 0; q < 6; ++q) s.scalars[8 + q] = (uint32_t)(gp_ph[q] >> 10);   // kilo-cycles per phase
+    s.scalars[15] = (uint32_t)(gp_ph[6] >> 10);
+    s.scalars[14] = (uint32_t)(gp_n / (unsigned long long)(in.n_steps > 0 ? in.n_steps : 1));   // mean candidates per step
+#endif
   }
 }
 

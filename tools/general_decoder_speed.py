@@ -43,6 +43,11 @@ def run(name, labels, scorer, probs, beam, cutoff):
     b.fetch()
     out[name] = {"utterances": B, "timesteps": T, "classes": C, "beam": beam, "cutoff": cutoff, "decode_ms": ms,
                  "us_per_timestep": 1000.0 * ms / T, "tokens_first": len(b.results(0)[0][1])}
+    if os.environ.get("STT_GEN_PROF"):   # variant build with phase clocks (-DSTT_GEN_PROF): kilo-cycles per phase, summed over utterances
+        sc = b.decoder_scalars()
+        out[name]["phase_kcycles"] = dict(zip(("row+cutoff+parents", "live_update", "children", "select", "compaction", "commit"), sc[8:14]))
+        out[name]["mean_candidates_per_step"] = sc[14] / float(B)
+        out[name]["phase_kcycles"]["children_count_pass"] = sc[15]
 
 
 rng = np.random.default_rng(1)
