@@ -500,6 +500,47 @@ __device__ double utf8_window_cond(const Slot& s, const DecodeParams& p, uint32_
   return sttscorer::log_cond_prob_ids(v, ids, n, n < order);
 }
 
+// The same value from the CARRIED KenLM state (the argument of lm_eval_node, with code points for words): the unit `wid`
+// scored from the state stored at its context node -- the node where the previous code point ended, whose lm_* rows were
+// filled when it was created -- or from BeginSentence at the root.  One trie descent instead of `order`.  Returns false
+// when the context carries no state (then the literal window above is evaluated).
+__device__ bool utf8_cond_carried(const Slot& s, const DecodeParams& p, uint32_t ctx, uint32_t wid, double* cond_out,
+                                  sttscorer::LmState* out, uint32_t* meta_out) {
+  const sttscorer::ScorerView& v = p.scorer;
+  const int order = (int)v.order;
+  sttscorer::LmState c;
+  uint32_t ctx_oov = 255, ctx_words = 0;
+  if (ctx == kNone || s.nodes[ctx].chr == kRootChar) {
+    sttscorer::begin_sentence_state(v, c);
+  } else {
+    const uint32_t meta = s.lm_meta[ctx];
+    if (meta == kNone) return false;
+    c.length = (uint8_t)(meta & 0xffu);
+    ctx_oov = (meta >> 8) & 0xffu;
+    ctx_words = meta >> 16;
+    for (int i = 0; i < (int)c.length && i < kStateWords; ++i) {
+      c.words[i] = s.lm_sw[(size_t)ctx * kStateWords + i];
+      c.backoff[i] = s.lm_sb[(size_t)ctx * kStateWords + i];
+    }
+  }
+  out->length = 0;
+  uint32_t oov_dist;
+  double cond;
+  if (wid == 0) {
+    sttscorer::null_context_state(*out);
+    oov_dist = 0;
+    cond = -1000.0;   // OOV_SCORE (scorer.cpp:328-331)
+  } else {
+    const float p10 = sttscorer::full_score(v, c, wid, *out);
+    oov_dist = ctx_oov >= 254 ? 255u : ctx_oov + 1;
+    cond = (oov_dist <= (uint32_t)(order - 1)) ? -1000.0 : (double)p10 / (double)0.4342944819f;
+  }
+  const uint32_t nwords = ctx_words >= 0xfffeu ? 0xffffu : ctx_words + 1;
+  *meta_out = (uint32_t)out->length | (oov_dist << 8) | (nwords << 16);
+  *cond_out = cond;
+  return true;
+}
+
 // LM term (before alpha) of an EXISTING node whose last byte completes a code point; cached in Slot::lm_cond.
 __device__ double utf8_node_cond(const Slot& s, const DecodeParams& p, uint32_t node) {
   if (p.n_hot == 0) {

@@ -233,8 +233,16 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
         uint32_t ord, ctx;
         utf8_child_fields(sv, pn, pi_node, c, &ord, &ctx);
         if (!utf8_completes(ord)) return 0.0f;
-        float boost = 0.0f;
-        cond = utf8_window_cond(s, p, pi_node, c, &boost) + (double)boost;
+        bool have = false;
+        if (p.n_hot == 0) {   // one descent from the carried state (hot words need the window's ids: literal path)
+          sttscorer::LmState out_unused;
+          uint32_t meta_unused;
+          have = utf8_cond_carried(s, p, ctx, utf8_unit_id(s, sv, pi_node, (ord & 0xffu) - 1u, c), &cond, &out_unused, &meta_unused);
+        }
+        if (!have) {
+          float boost = 0.0f;
+          cond = utf8_window_cond(s, p, pi_node, c, &boost) + (double)boost;
+        }
       }
       *scored = true;
       return (float)(cond * sv.alpha);
@@ -501,11 +509,29 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
           n.lm_wid = kNone;
           n.child_mask = 0;
           uint32_t meta_init = kNone;
+          double cond_init = 0.0;
+          bool cond_known = false;
           if (utf8) {
             uint32_t ord, ctx;
             utf8_child_fields(sv, par, pnode, c, &ord, &ctx);
             n.ord = ord;
             n.last_space = ctx;
+            if (p.has_scorer && utf8_completes(ord)) {
+              // this node ends a code point: its LM term and the KenLM state after it (the context of the next code
+              // point) are computed once, here
+              const uint32_t wid = utf8_unit_id(s, sv, pnode, (ord & 0xffu) - 1u, c);
+              sttscorer::LmState st_out;
+              uint32_t meta_out;
+              if (utf8_cond_carried(s, p, ctx, wid, &cond_init, &st_out, &meta_out)) {
+                for (int q = 0; q < (int)st_out.length && q < kStateWords; ++q) {
+                  s.lm_sw[(size_t)id * kStateWords + q] = st_out.words[q];
+                  s.lm_sb[(size_t)id * kStateWords + q] = st_out.backoff[q];
+                }
+                meta_init = meta_out;
+                cond_known = true;
+                n.lm_wid = wid;
+              }
+            }
           } else {
             n.last_space = is_space ? id : par.last_space;
             n.word_id = 0;
@@ -529,7 +555,8 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
           }
           s.nodes[id] = n;
           s.lm_meta[id] = meta_init;
-          reinterpret_cast<unsigned long long*>(s.lm_cond)[id] = kLmUnset;
+          if (cond_known) s.lm_cond[id] = cond_init;
+          else reinterpret_cast<unsigned long long*>(s.lm_cond)[id] = kLmUnset;
           ht_insert(s, pnode, c, id);
           atomicOr(&s.nodes[pnode].child_mask, 1u << (c & 31u));
         }
