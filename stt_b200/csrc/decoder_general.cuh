@@ -26,6 +26,7 @@ struct GenParams {
   double cutoff_prob;
   int cutoff_top_n;
   uint32_t* scratch;     // kGenScratchArrays arrays of beam_cap words per utterance
+  const uint32_t* byte_wid;   // UTF-8 scorers: vocabulary id of every ONE-byte code point (0 = not in the vocabulary), [256]
 };
 constexpr int kGenScratchArrays = 12;
 
@@ -237,7 +238,10 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
         if (p.n_hot == 0) {   // one descent from the carried state (hot words need the window's ids: literal path)
           sttscorer::LmState out_unused;
           uint32_t meta_unused;
-          have = utf8_cond_carried(s, p, ctx, utf8_unit_id(s, sv, pi_node, (ord & 0xffu) - 1u, c), &cond, &out_unused, &meta_unused);
+          // a one-byte code point's vocabulary id is a table read (engine.cu builds the table when the scorer is enabled)
+          const uint32_t wid = ((ord & 0xffu) == 1u && g.byte_wid && sv.label_len[c] == 1) ? g.byte_wid[sv.label_bytes[c][0]]
+                                                                                          : utf8_unit_id(s, sv, pi_node, (ord & 0xffu) - 1u, c);
+          have = utf8_cond_carried(s, p, ctx, wid, &cond, &out_unused, &meta_unused);
         }
         if (!have) {
           float boost = 0.0f;
@@ -519,7 +523,8 @@ __global__ void __launch_bounds__(NT) decoder_general_kernel(Slot* slots, const 
             if (p.has_scorer && utf8_completes(ord)) {
               // this node ends a code point: its LM term and the KenLM state after it (the context of the next code
               // point) are computed once, here
-              const uint32_t wid = utf8_unit_id(s, sv, pnode, (ord & 0xffu) - 1u, c);
+              const uint32_t wid = ((ord & 0xffu) == 1u && g.byte_wid && sv.label_len[c] == 1) ? g.byte_wid[sv.label_bytes[c][0]]
+                                                                                              : utf8_unit_id(s, sv, pnode, (ord & 0xffu) - 1u, c);
               sttscorer::LmState st_out;
               uint32_t meta_out;
               if (utf8_cond_carried(s, p, ctx, wid, &cond_init, &st_out, &meta_out)) {

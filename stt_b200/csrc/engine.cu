@@ -192,10 +192,11 @@ struct DeviceScorer {
   uint32_t* ord2wid = nullptr;
   uint2* gstate = nullptr;             // general kernel (decoder_general.cuh): per state {first arc, number of arcs}
   int2* garc = nullptr;                //                                        per arc {label, child dictionary state}
+  uint32_t* byte_wid = nullptr;        // UTF-8 scorers: vocabulary id of each one-byte code point [256]
   std::vector<uint8_t> vocab_host;     // the vocabulary-hash section, kept on the host for hot-word id lookups
   ~DeviceScorer() {
     cudaSetDevice(device);
-    for (void* p : {(void*)blob, (void*)fst_state2, (void*)fst_arc4, (void*)fst_space_skip, (void*)ord2wid, (void*)gstate, (void*)garc})
+    for (void* p : {(void*)blob, (void*)fst_state2, (void*)fst_arc4, (void*)fst_space_skip, (void*)ord2wid, (void*)gstate, (void*)garc, (void*)byte_wid})
       if (p) cudaFree(p);
   }
 };
@@ -624,6 +625,19 @@ int engine_set_scorer(Engine* e, const uint8_t* bytes, size_t n) {
       cudaMemcpy(ds->garc, gar.data(), gar.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();
     return sttscorer::SCORER_UNREADABLE;
+  }
+  if (v.is_utf8) {
+    // one-byte code points (ASCII): vocabulary ids looked up once; v.blob still addresses the host copy here
+    std::vector<uint32_t> bw(256, 0);
+    for (int bt = 1; bt < 128; ++bt) {
+      const uint8_t ch = (uint8_t)bt;
+      bw[bt] = sttscorer::vocab_index(v, &ch, 1);
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&ds->byte_wid), 256 * 4) != cudaSuccess ||
+        cudaMemcpy(ds->byte_wid, bw.data(), 256 * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      return sttscorer::SCORER_UNREADABLE;
+    }
   }
   ds->blob_bytes = n;
   const size_t vocab_end = std::min<size_t>(n, (size_t)(v.probing ? v.pvocab_off + v.pvocab_buckets * 12 + 16
@@ -1322,6 +1336,7 @@ int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& i
     gp.cutoff_prob = b->cutoff_prob;
     gp.cutoff_top_n = b->cutoff_top_n;
     gp.scratch = b->d_gen_scratch;
+    gp.byte_wid = sc ? sc->byte_wid : nullptr;
     dp.fst_space_skip = nullptr;   // the general kernel does not maintain word ordinals: words are hashed
     dp.ord2wid = nullptr;
     sttdec::decoder_general_kernel<256><<<n_slots, 256, 0, st>>>(b->d_slots, b->d_inputs, dp, gp);
