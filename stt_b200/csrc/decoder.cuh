@@ -666,15 +666,13 @@ struct StepSmem {
   uint32_t p0[NC > 0 ? WC : 1], p1[NC > 0 ? WC : 1];
 };
 
-// kInstr compiles in the per-phase clocks and LM counters (bench statistics).  Two CTAs per SM for beams <= 512 (the
-// register budget follows from that), one for the wide instantiation.
-template <int NT, int WC, int NC, bool kInstr>
-#ifndef STT_DEC_MINBLOCKS   // A/B builds only (Makefile `variant`)
-#define STT_DEC_MINBLOCKS 2
-#endif
-// Measured alternatives (round 2, B200): 256 threads with two prefixes each (128 registers, no spills) 9.3 ms vs 8.8;
-// one CTA per SM with 128 registers 6.35 ms alone but two waves for 256 utterances; 384 threads neutral (round 1).
-__global__ void __launch_bounds__(NT, (WC <= 512 ? STT_DEC_MINBLOCKS : 1))
+// kInstr compiles in the per-phase clocks and LM counters (bench statistics).
+// MINB = CTAs per SM the register budget is sized for: 2 (64 registers) when a batch needs two CTAs per SM, 1 (128 registers:
+// no spills, no re-materialised thread ids -- 6.35 ms instead of 8.0 for 128 utterances) when it fits one CTA per SM.
+// Measured alternatives (round 2, B200): 256 threads with two prefixes each (128 registers) 9.3 ms vs 8.8 for 256 utterances;
+// 384 threads neutral (round 1).
+template <int NT, int WC, int NC, bool kInstr, int MINB = 2>
+__global__ void __launch_bounds__(NT, (WC <= 512 ? MINB : 1))
 decoder_step_kernel(Slot* slots, const StepInput* inputs, const DecodeParams p) {
   static_assert(NT == 512 || NT == 256, "phase 6: 128 (round, warp) counts, four per lane of the scanning warps");
   constexpr int kCommitRounds = kCommitSpan / NT;   // candidate rounds (of NT) compacted per scan in phase 6

@@ -115,7 +115,7 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t co
 // on its device in a bit mask.  Setting an attribute twice is harmless, so concurrent host threads need no lock.
 enum KernelBit {
   kBitGemmWin = 0, kBitGemmRelu, kBitGemmBias, kBitGemmSoftmax, kBitGemmSoftmaxWide, kBitDecGeneral, kBitGemm2Relu, kBitGemm2Bias, kBitLstm1, /* +0..3 by cluster size */ kBitLstm2 = kBitLstm1 + 4,
-  kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitLstmPP4Mc, kBitLstmPP4Mc4, kBitDec512, kBitDec512I, kBitDec2048, kBitDec2048I
+  kBitLstmPair = kBitLstm2 + 4, kBitLstmPP4, kBitLstmPP2, kBitLstmPP1, kBitLstmPP4Mc, kBitLstmPP4Mc4, kBitDec512Solo, kBitDec512, kBitDec512I, kBitDec2048, kBitDec2048I
 };
 template <class K>
 int ensure_smem(std::atomic<uint32_t>* mask, int bit, K kern, int bytes) {
@@ -1352,8 +1352,10 @@ int decoder_steps(Batch* b, int n_slots, const std::vector<sttdec::StepInput>& i
   int rc;
   if (b->beam_cap <= 512) {
     constexpr size_t SM = sizeof(sttdec::StepSmem<512, 5632>);
-    rc = b->instrument ? go(sttdec::decoder_step_kernel<NT, 512, 5632, true>, kBitDec512I, SM)
-                       : go(sttdec::decoder_step_kernel<NT, 512, 5632, false>, kBitDec512, SM);
+    if (b->instrument) rc = go(sttdec::decoder_step_kernel<NT, 512, 5632, true>, kBitDec512I, SM);
+    else if (n_slots <= e->num_sms)   // one CTA per SM anyway: the 128-register build (streams, small batches)
+      rc = go(sttdec::decoder_step_kernel<NT, 512, 5632, false, 1>, kBitDec512Solo, SM);
+    else rc = go(sttdec::decoder_step_kernel<NT, 512, 5632, false>, kBitDec512, SM);
   } else if (b->beam_cap <= 2048) {
     constexpr size_t SM = sizeof(sttdec::StepSmem<2048, 0>);
     rc = b->instrument ? go(sttdec::decoder_step_kernel<NT, 2048, 0, true>, kBitDec2048I, SM)
