@@ -67,9 +67,16 @@ class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []          # (time read, fields)
+        self.windows = []       # [t0, t1] of the timed regions: only samples taken inside them are reported
         self.proc = None
         self.gpu = gpu_index
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.perf_counter()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -77,7 +84,7 @@ class ClockSampler(object):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -86,7 +93,7 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -96,10 +103,14 @@ class ClockSampler(object):
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if any(w[0] <= t <= (w[1] or t) for w in self.windows)]
+        if not inside and self.rows:   # a timed region shorter than the sampling period: the sample nearest to it
+            mid = 0.5 * (self.windows[0][0] + (self.windows[-1][1] or self.windows[-1][0])) if self.windows else self.rows[-1][0]
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - mid))[1]]
+        sm = [float(r[0]) for r in inside if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in inside:
             if len(r) >= 7:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
@@ -240,12 +251,13 @@ def main():
         t = batch.timings()
         return t
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()             # nvidia-smi needs a moment to come up: started before the warm-up, read inside the timed regions
     for _ in range(args.warmup):
         device_step()
     launches0 = batch.kernel_launches()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.begin()
     stage_sum = {}
     wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -254,7 +266,7 @@ def main():
             stage_sum[k] = stage_sum.get(k, 0.0) + v
     barrier()
     wall_dev = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    sampler.end()
     launches = (batch.kernel_launches() - launches0) // args.steps
     stages = {k: v / args.steps for k, v in stage_sum.items()}
     dev_keys = ("mfcc", "dense123", "lstm_in", "lstm", "dense56", "decode")
@@ -277,10 +289,13 @@ def main():
         pinned.append(rows)
     pipe.map([pinned[i % E2E_DEPTH] for i in range(E2E_DEPTH)])   # warm both contexts
     barrier()
+    sampler.begin()
     w0 = time.perf_counter()
     texts = pipe.map([pinned[i % E2E_DEPTH] for i in range(args.steps)])[-1]
     barrier()
     e2e_wall = max_over_ranks((time.perf_counter() - w0) / args.steps)
+    sampler.end()
+    clocks = sampler.stop()
     e2e_value = audio_per_step / e2e_wall
     # ---- the same call a reference user would make, with ORDINARY (pageable) caller buffers and no pipelining:
     #      STTX_SpeechToTextBatch stages the PCM into pinned memory itself (an extra 82 MB host copy per step)
