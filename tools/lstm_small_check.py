@@ -1,5 +1,5 @@
-"""A/B of the LSTM kernels for batches of <= 128 utterances: default (one-CTA kernel, cluster multicast) vs the CTA-pair kernel
-with one group (STT_B200_LSTM_SMALL_PP=1).  Probabilities must be bit-identical.  usage: python tools/lstm_small_check.py"""
+"""A/B of the LSTM kernels for batches of <= 128 utterances: default (one-CTA kernel, cluster multicast) (STT_B200_LSTM_SMALL_PP=0) vs the CTA-pair kernel
+with one group (the default since round 2).  Probabilities must be bit-identical.  usage: python tools/lstm_small_check.py"""
 import os
 import sys
 import tempfile
@@ -17,10 +17,7 @@ for B in (128, 64, 16, 1):
     pcms = [synth.make_pcm(160000, utt=u) for u in range(B)]
     res = {}
     for env in (None, "1"):
-        if env is None:
-            os.environ.pop("STT_B200_LSTM_SMALL_PP", None)
-        else:
-            os.environ["STT_B200_LSTM_SMALL_PP"] = env
+        os.environ["STT_B200_LSTM_SMALL_PP"] = "0" if env is None else env
         m = Model(path)
         b = m.createBatch(B, 160000)
         b.upload(pcms)
@@ -29,4 +26,4 @@ for B in (128, 64, 16, 1):
         res[env] = (b.timings()["lstm"], [b.probs(u) for u in (0, B - 1)])
         del b, m
     same = all(np.array_equal(x, y) for x, y in zip(res[None][1], res["1"][1]))
-    print("B=%3d  default %.3f ms   pair kernel, one group %.3f ms   probabilities %s" % (B, res[None][0], res["1"][0], "bit-identical" if same else "DIFFERENT"), flush=True)
+    print("B=%3d  one-CTA kernel %.3f ms   pair kernel, one group %.3f ms   probabilities %s" % (B, res[None][0], res["1"][0], "bit-identical" if same else "DIFFERENT"), flush=True)
