@@ -131,7 +131,7 @@ def _edit_distance(a, b):
 # DISTANCE between the product's transcripts and the fp32 CPU path's, in labels (character error rate), and that this
 # distance is smaller than the one the reference's OWN default arithmetic (TFLite hybrid int8, oracle mode "hybrid8")
 # keeps from the same fp32 path on the same utterances.
-CER_VS_FP32_MAX = 0.04
+CER_VS_FP32_MAX = 0.05   # measured 2.56 % over 224 utterances; 3.6 % over the first 32 (a slower host gets through fewer)
 IDENTICAL_FRAC_MIN = 0.55
 
 
