@@ -135,3 +135,20 @@ def test_reference_cli_runs_on_our_library(small_model):
         r = subprocess.run([REF_CLI, "--model", path, "--audio", os.path.join(ROOT, "tests", "golden", "LDC93S1_pcms16le_1_16000.wav")],
                            capture_output=True, text=True, timeout=60)
         assert r.returncode != 0 and "Could not create model" in r.stderr
+
+
+def test_library_runs_on_tcgen05_tma_not_on_legacy_mma():
+    """The built product library's SASS (sm_100a): tcgen05.mma incl. cta_group::2 pairs, TMEM loads, TMA loads -- and no
+    legacy mma.sync (HMMA), no cuBLAS / cuDNN dependency.  B200_PROFILING.md names the mnemonics."""
+    import shutil
+    from stt_b200 import api
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", api.lib_path()], capture_output=True, text=True).stdout
+    n_mma = len(re.findall(r"\bUTC[A-Z]*MMA", sass))
+    n_pair = len(re.findall(r"\bUTC[A-Z]*MMA\.2CTA", sass))
+    assert n_mma >= 100 and n_pair >= 50, (n_mma, n_pair)
+    assert len(re.findall(r"\bLDTM", sass)) >= 10 and len(re.findall(r"\bUTMALDG", sass)) >= 100
+    assert not re.search(r"\bHMMA", sass)
+    needed = subprocess.run(["readelf", "-d", api.lib_path()], capture_output=True, text=True).stdout
+    assert "cublas" not in needed.lower() and "cudnn" not in needed.lower() and "torch" not in needed.lower()
