@@ -221,3 +221,54 @@ def test_decoder_with_every_kenlm_trie_layout(ref_decoder, small_model, english,
     for u in range(B):
         ref = o.ref_decode(probs[u], alpha, 128, sc, num_results=3)
         _compare(b.results(u), ref, "layout=%s utt=%d" % (layout, u))
+
+
+@pytest.mark.parametrize("order,kind,seed", [(2, "trie", 1), (2, "probing", 2), (3, "quant_array_trie", 3), (3, "array_trie", 4),
+                                             (6, "quant_array_trie", 5), (6, "probing", 6), (6, "quant_trie", 7),
+                                             (4, "probing", 8)])
+def test_decoder_with_random_lms_of_every_order(ref_decoder, small_model, english, tmp_path, order, kind, seed):
+    """Randomised KenLM models of order 2, 3 and 6 (KENLM_MAX_ORDER; the committed fixtures are orders 4 and 5), built on
+    the spot with the reference's build_binary (oracle/_ref, test_scorer_fuzz.py's generator) and packaged by the
+    reference's Scorer: the carried KenLM state holds order-1 words, so the state hand-over between a prefix's words is
+    exercised at its shortest and longest -- shared-memory kernel and, with vocabulary pruning, the general kernel."""
+    import subprocess
+    from test_scorer_fuzz import BUILD_BINARY, _flags, _random_arpa
+    from stt_b200 import Model, synth
+    if not os.path.exists(BUILD_BINARY):
+        pytest.skip("oracle/_ref/build_binary not built")
+    o = ref_decoder
+    rng = np.random.default_rng(seed)
+    arpa = str(tmp_path / "lm.arpa")
+    words, got_order = _random_arpa(rng, arpa, order, 60, 500, 0.25 if seed % 2 else 0.0)
+    assert got_order == order
+    typ, flags = _flags(rng, kind)
+    lm = str(tmp_path / "lm.binary")
+    subprocess.check_call([BUILD_BINARY] + flags + ["-v"] + typ + [arpa, lm], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    alpha = o.RefAlphabet(english)
+    pkg = str(tmp_path / "lm.scorer")
+    assert o.ref().ref_make_scorer_package(lm.encode(), b"".join(w.encode() + b"\0" for w in words), len(words),
+                                           alpha.h, pkg.encode(), 0.8, 1.4) == 0
+    sc = o.RefScorer(pkg, alpha)
+    path, _ = small_model
+    m = Model(path)
+    m.setBeamWidth(96)
+    m.enableExternalScorer(pkg)
+    B, T = 4, 140
+    probs = np.stack([synth.make_ctc_probs(words, T, utt=7300 + 10 * seed + u) for u in range(B)])
+    b = m.createBatch(B, T * 320)
+    b.set_probs(probs, [T] * B)
+    b.decode(num_results=3)
+    b.fetch()
+    for u in range(B):
+        ref = o.ref_decode(probs[u], alpha, 96, sc, num_results=3)
+        _compare(b.results(u), ref, "order=%d %s utt=%d" % (order, kind, u))
+    b2 = m.createBatch(B, T * 320)
+    b2.set_probs(probs, [T] * B)
+    b2.set_cutoff(0.995, 12)
+    b2.decode(num_results=2)
+    b2.fetch()
+    for u in range(B):
+        ref = o.ref_decode(probs[u], alpha, 96, sc, num_results=2, cutoff_prob=0.995, cutoff_top_n=12)
+        for (gc, gt, gts), (rc, rt, rts) in zip(b2.results(u), ref):
+            assert list(gt) == list(rt) and list(gts) == list(rts), "pruned order=%d %s utt=%d" % (order, kind, u)
+            assert gc == rc or rc < -1e30

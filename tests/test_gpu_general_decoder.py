@@ -313,3 +313,37 @@ def test_general_kernel_wide_beam(ref_decoder):
     rng = np.random.default_rng(31)
     probs, lens = _batch(_byte_seqs(["señormüller", "東京タワー"]), 256, rng, noise=0.05)
     _compare(o, m, ra, rs, probs, lens, 1500, 2, 1.0, 40, "bytes wide beam")
+
+
+@pytest.mark.parametrize("order,kind,seed", [(2, "quant_array_trie", 21), (6, "quant_array_trie", 22), (6, "probing", 23), (3, "trie", 24)])
+def test_bytes_mode_random_lms_of_every_order(ref_decoder, tmp_path, order, kind, seed):
+    """UTF-8 scorers over random code-point models of order 2, 3 and 6 (the committed bytes fixtures are orders 3 and 5):
+    the KenLM state carried from code point to code point holds order-1 units; built with the reference's build_binary
+    and packaged by the reference's Scorer in UTF-8 mode."""
+    import subprocess
+    from test_scorer_fuzz import BUILD_BINARY, _flags, _random_arpa
+    if not os.path.exists(BUILD_BINARY):
+        pytest.skip("oracle/_ref/build_binary not built")
+    o = ref_decoder
+    rng = np.random.default_rng(seed)
+    units = list("abcdefghijklmnop") + list("éñüßøж") + list("日本語の한국") + list("😀🚀💙")
+    arpa = str(tmp_path / "lm.arpa")
+    words, got_order = _random_arpa(rng, arpa, order, len(units), 400, 0.2 if seed % 2 else 0.0, words=set(units))
+    assert got_order == order
+    typ, flags = _flags(rng, kind)
+    lm = str(tmp_path / "lm.binary")
+    subprocess.check_call([BUILD_BINARY] + flags + ["-v"] + typ + [arpa, lm], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ra = o.RefByteAlphabet()
+    pkg = str(tmp_path / "lm.bytes.scorer")
+    assert o.ref().ref_make_scorer_package_utf8(lm.encode(), b"".join(w.encode("utf-8") + b"\0" for w in words), len(words),
+                                                ra.h, pkg.encode(), 0.85, 1.2) == 0
+    rs = o.RefScorer(pkg, ra)
+    assert o.ref().ref_scorer_is_utf8(rs.h) == 1 and o.ref().ref_scorer_max_order(rs.h) == order
+    m = _host_model(BYTE_LABELS, pkg)
+    texts = ["".join(words[int(i)] for i in np.minimum((rng.pareto(1.1, int(rng.integers(1, 14))) * 3).astype(np.int64), len(words) - 1))
+             for _ in range(10)]
+    all_bytes = np.array(sorted({b - 1 for t in units for b in t.encode("utf-8")}))
+    probs, lens = _batch(_byte_seqs(texts), 256, rng, noise=0.02, confuse=all_bytes)
+    for beam in (8, 100):
+        for cp, tn in ((1.0, 40), (1.0, 256), (0.99, 40)):
+            _compare(o, m, ra, rs, probs, lens, beam, 3, cp, tn, "bytes random order %d %s" % (order, kind))

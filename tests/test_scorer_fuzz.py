@@ -18,14 +18,16 @@ BUILD_BINARY = os.path.join(ROOT, "oracle", "_ref", "build_binary")
 LETTERS = "abcdefghijklmnopqrstuvwxyz'"
 
 
-def _random_arpa(rng, path, order, n_words, n_sent, prune):
+def _random_arpa(rng, path, order, n_words, n_sent, prune, words=None):
     """An ARPA file over random sentences: all contiguous n-grams up to `order` (so every context and every suffix is
     present), random log10 probabilities and backoffs; `prune` drops a share of the order >= 2 entries afterwards
     (entries of the highest order and contexts of surviving entries alike -- what lmplz --prune leaves behind)."""
-    words = set()
-    while len(words) < n_words:
-        words.add("".join(LETTERS[int(i)] for i in rng.integers(0, len(LETTERS), int(rng.integers(1, 7)))))
+    if words is None:
+        words = set()
+        while len(words) < n_words:
+            words.add("".join(LETTERS[int(i)] for i in rng.integers(0, len(LETTERS), int(rng.integers(1, 7)))))
     words = sorted(words)
+    n_words = len(words)
     grams = [set() for _ in range(order)]
     for _ in range(n_sent):
         k = int(rng.integers(1, 11))
@@ -50,7 +52,7 @@ def _random_arpa(rng, path, order, n_words, n_sent, prune):
                 grams[n - 2].add(g[:-1])
     while order > 1 and not grams[order - 1]:
         order -= 1
-    with open(path, "w") as f:
+    with open(path, "w", encoding="utf-8") as f:
         f.write("\\data\\\n")
         for n in range(1, order + 1):
             f.write("ngram %d=%d\n" % (n, len(grams[n - 1])))
