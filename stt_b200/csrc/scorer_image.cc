@@ -103,6 +103,12 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
   std::vector<uint64_t> counts(order);
   if (pos + 8ull * order > size) return SCORER_INVALID_LM;
   memcpy(counts.data(), file + pos, 8ull * order);
+  // a record takes at least one bit: counts beyond 8 * size cannot belong to this file (and would overflow the size
+  // arithmetic below); counts[0] includes <unk>, so it is at least 1
+  if (size > (1ull << 48)) return SCORER_INVALID_LM;
+  for (uint64_t c : counts)
+    if (c > 8ull * size) return SCORER_INVALID_LM;
+  if (counts[0] == 0 || counts[0] > 0xffffffffull) return SCORER_INVALID_LM;   // WordIndex is 32 bits
   const uint64_t header_size = ((kSanity + 20 + 8ull * order - 1) / 8 + 1) * 8;  // ALIGN8
 
   v->order = order;
@@ -111,28 +117,48 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
     // ---- probing-hash model (search_hashed.cc:206-220, vocab.cc:270-283): [vocabulary header 8 B + table of 12-byte
     //      entries][unigram weights x (count + 1)][middle tables, 8 + weights bytes per entry][longest table, 12 bytes]
     //      every table holds max(entries + 1, multiplier * entries) buckets (probing_hash_table.hh:108-111)
-    if (!(probing_multiplier >= 1.0f)) return SCORER_INVALID_LM;
+    if (!(probing_multiplier >= 1.0f) || !(probing_multiplier <= 1024.0f)) return SCORER_INVALID_LM;
     auto buckets_for = [&](uint64_t entries) {
-      const uint64_t scaled = (uint64_t)(probing_multiplier * (float)entries);
+      const uint64_t scaled = (uint64_t)(probing_multiplier * (float)entries);   // entries <= 2^51, multiplier <= 2^10
       return std::max<uint64_t>(entries + 1, scaled);
+    };
+    // a table must lie inside the file before it is probed; linear probing (probing_hash_table.hh:150-165) ends at an
+    // empty bucket (key 0), so every table must hold one or a lookup would never return
+    auto table_ok = [&](uint64_t off, uint64_t buckets, uint64_t entry_bytes) {
+      if (buckets > size / entry_bytes || off > size || buckets * entry_bytes > size - off) return false;
+      for (uint64_t i = 0; i < buckets; ++i) {
+        uint64_t key;
+        memcpy(&key, file + off + i * entry_bytes, 8);
+        if (key == 0) return true;
+      }
+      return false;
     };
     v->probing = model_type == 0 ? 1 : 2;
     v->weights_size = model_type == 0 ? 8 : 12;
     uint64_t p = header_size;
     v->pvocab_buckets = buckets_for(counts[0]);
     v->pvocab_off = p + 8;
+    if (header_size + 8 > size || !table_ok(v->pvocab_off, v->pvocab_buckets, 12)) return SCORER_INVALID_LM;
+    for (uint64_t i = 0; i < v->pvocab_buckets; ++i) {   // {u64 hash, u32 word id}: ids index the unigram array
+      uint32_t id;
+      memcpy(&id, file + v->pvocab_off + i * 12 + 8, 4);
+      if (id >= counts[0]) return SCORER_INVALID_LM;
+    }
     p += 8 + v->pvocab_buckets * 12;
     v->vocab_off = v->pvocab_off;      // start of the vocabulary section (hot-word lookups keep a host copy up to here)
     v->vocab_count = counts[0];        // word ids are < counts[0]
     v->unigram_off = p;
     p += (counts[0] + 1) * v->weights_size;
+    if (p > size) return SCORER_INVALID_LM;
     for (int i = 2; i < order; ++i) {
       v->ptab_off[i - 2] = p;
       v->ptab_buckets[i - 2] = buckets_for(counts[i - 1]);
+      if (!table_ok(p, v->ptab_buckets[i - 2], 8 + v->weights_size)) return SCORER_INVALID_LM;
       p += v->ptab_buckets[i - 2] * (8 + v->weights_size);
     }
     v->ptab_off[order - 2] = p;
     v->ptab_buckets[order - 2] = buckets_for(counts[order - 1]);
+    if (!table_ok(p, v->ptab_buckets[order - 2], 12)) return SCORER_INVALID_LM;
     p += v->ptab_buckets[order - 2] * 12;
     trie_offset = p;
     if (size <= trie_offset) return SCORER_NO_TRIE;
@@ -266,11 +292,14 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
   const bool aligned = (flags & 4) || fversion == 1;
   if (aligned) pos = (pos + 15) & ~15ull;
   v->fst_states_off = pos;
+  // bounds first: the products below must not wrap
+  if (numstates < 0 || numarcs < 0 || (uint64_t)numstates > size / 20 || (uint64_t)numarcs > size / 16) return SCORER_INVALID_TRIE;
+  if (start < -1 || start >= numstates) return SCORER_INVALID_TRIE;   // kNoStateId = -1: an empty automaton
   pos += (uint64_t)numstates * 20;
   if (aligned) pos = (pos + 15) & ~15ull;
   v->fst_arcs_off = pos;
   pos += (uint64_t)numarcs * 16;
-  if (pos > size || numstates < 0 || numarcs < 0) return SCORER_INVALID_TRIE;
+  if (pos > size) return SCORER_INVALID_TRIE;
   v->fst_start = start;
   v->fst_nstates = numstates;
   v->fst_narcs = numarcs;

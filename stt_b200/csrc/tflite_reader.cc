@@ -159,10 +159,12 @@ struct Graph {
   }
   // constant behind `ti`: its own buffer, or the first constant input of the operator chain that produces it
   // (the reference runs those operators once: tflitemodelstate.cc:226-262)
+  int visits = 0;   // bound on the walk below: a crafted graph must not make it exponential
   int constant_source(int ti, int depth = 0) {
+    if (depth == 0) visits = 0;
     size_t nbytes;
     if (data(ti, &nbytes) && nbytes) return ti;
-    if (depth > 4) return -1;
+    if (depth > 4 || ++visits > 4096) return -1;
     const int k = producer(ti);
     if (k < 0) return -1;
     for (int32_t in : ops[k].in) {
@@ -271,6 +273,9 @@ bool read_floats(Graph* g, int ti, size_t count, std::vector<float>* out) {
     if (!d || !nbytes) return false;
   }
   const Tensor& T = g->tensors[src];
+  // the byte count is checked BEFORE anything is allocated: `count` comes from shape fields of the file
+  const size_t elem = T.type == kTypeF32 ? 4 : T.type == kTypeF16 ? 2 : T.type == kTypeI8 ? 1 : 0;
+  if (!elem || count > nbytes || nbytes != count * elem) return false;
   out->resize(count);
   if (T.type == kTypeF32) {
     if (nbytes != count * 4) return false;
@@ -403,11 +408,15 @@ int load_tflite(const uint8_t* data, size_t size, HostModel* m) {
   for (const Op& op : g.ops) {
     if (op.code != kOpFullyConnected || op.in.size() < 2) continue;
     const int w = op.in[1], b = op.in.size() > 2 ? op.in[2] : -1;
+    if (w < 0 || (size_t)w >= g.tensors.size() || (b >= 0 && (size_t)b >= g.tensors.size())) {
+      fprintf(stderr, "Model file: a FULLY_CONNECTED operator refers to a tensor that does not exist.\n");
+      return kIncompatible;
+    }
     bool seen = false;
     for (const Fc& f : fcs) {
       if (f.w == w) seen = true;
       // the unrolled LSTM may carry one copy of the kernel per timestep: same buffer or same bytes
-      if (!seen && w >= 0 && f.w >= 0 && (size_t)w < g.tensors.size() && g.tensors[w].shape == g.tensors[f.w].shape) {
+      if (!seen && g.tensors[w].shape == g.tensors[f.w].shape) {
         size_t n1, n2;
         const uint8_t* d1 = g.data(g.constant_source(w), &n1);
         const uint8_t* d2 = g.data(g.constant_source(f.w), &n2);
