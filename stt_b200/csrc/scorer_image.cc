@@ -62,6 +62,66 @@ bool rd_string(const uint8_t* file, size_t size, uint64_t& pos, std::string* out
   return true;
 }
 
+// Every child range a lookup can obtain must lie inside the next level: the search functions of scorer_view.h (host
+// and device) index records with whatever the parent's `next` pointers say, so a damaged record would send them
+// outside the file -- on the GPU, an illegal address that takes the CUDA context down.  One sequential pass per level:
+// the pointers (inline bits + ArrayBhiksha high part, bhiksha.hh:76-97) must be non-decreasing and end inside the
+// next level; KenLM itself trusts the file here (trie.cc:74-99).
+bool trie_pointers_ok(const ScorerView& v, const std::vector<uint64_t>& counts) {
+  const int order = (int)v.order;
+  {  // unigrams: `next` of words 0 .. counts[0] (the last one is the end pointer, search_trie.cc:517-518)
+    const uint8_t* u = v.blob + v.unigram_off;
+    uint64_t prev = 0;
+    for (uint64_t w = 0; w <= counts[0]; ++w) {
+      const uint64_t nx = load_u64(u + w * 16 + 8);
+      if (nx < prev) return false;
+      prev = nx;
+    }
+    if (prev > counts[1]) return false;
+  }
+  for (int i = 2; i < order; ++i) {
+    const MiddleView& m = v.middle[i - 2];
+    const uint8_t* base = v.blob + m.records_off;
+    const uint8_t* offs = v.blob + m.offsets_off;
+    if (v.bhiksha) {
+      uint64_t prev = 0;
+      for (uint64_t k = 0; k < m.offsets_count; ++k) {
+        const uint64_t x = load_u64(offs + k * 8);
+        if (x < prev || (k == 0 && x != 0)) return false;
+        prev = x;
+      }
+      if (m.offsets_count == 0 || m.next_bits >= 57) return false;
+    }
+    uint64_t prev = 0, ub = 0;
+    const uint64_t next_at = (uint64_t)m.word_bits + m.quant_bits;
+    for (uint64_t r = 0; r <= m.n_records; ++r) {
+      uint64_t nx = read_int57(base, r * m.total_bits + next_at, m.next_mask);
+      if (v.bhiksha) {
+        while (ub < m.offsets_count && load_u64(offs + ub * 8) <= r) ++ub;   // ub = #offsets <= r  (>= 1: offsets[0] == 0)
+        nx |= (ub - 1) << m.next_bits;
+      }
+      if (nx < prev) return false;
+      prev = nx;
+    }
+    if (prev > counts[i]) return false;
+  }
+  return true;
+}
+
+// ConstFst body: every state's arc span inside the arc array, every arc's target a state (const-fst.h:102-110)
+bool fst_body_ok(const uint8_t* file, const ScorerView& v) {
+  for (int64_t q = 0; q < v.fst_nstates; ++q) {
+    const uint8_t* srec = file + v.fst_states_off + (uint64_t)q * 20;
+    const uint64_t pos = load_u32(srec + 4), narcs = load_u32(srec + 8);
+    if (pos + narcs > (uint64_t)v.fst_narcs) return false;
+  }
+  for (int64_t a = 0; a < v.fst_narcs; ++a) {
+    const int32_t nx = (int32_t)load_u32(file + v.fst_arcs_off + (uint64_t)a * 16 + 12);
+    if (nx < 0 || nx >= v.fst_nstates) return false;
+  }
+  return true;
+}
+
 }  // namespace
 
 int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet, ScorerView* v) {
@@ -252,6 +312,10 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
 
   // <s>, </s>, begin-sentence backoff (model.cc:78-84)
   v->blob = file;  // temporarily host-addressed so the view functions can be used for setup
+  if (!trie_pointers_ok(*v, counts)) {
+    v->blob = nullptr;
+    return SCORER_INVALID_LM;
+  }
   v->bos_word = vocab_index(*v, reinterpret_cast<const uint8_t*>("<s>"), 3);
   v->eos_word = vocab_index(*v, reinterpret_cast<const uint8_t*>("</s>"), 4);
   {
@@ -303,6 +367,10 @@ int parse_scorer(const uint8_t* file, size_t size, const AlphabetBytes& alphabet
   v->fst_start = start;
   v->fst_nstates = numstates;
   v->fst_narcs = numarcs;
+  if (!fst_body_ok(file, *v)) {
+    v->blob = nullptr;
+    return SCORER_INVALID_TRIE;
+  }
 
   // ---- alphabet bytes
   v->n_labels = (uint32_t)alphabet.labels.size();

@@ -14,10 +14,32 @@
 #include "../../stt_b200/csrc/model_file.h"
 #include "../../stt_b200/csrc/scorer_image.h"
 
+static std::mt19937_64 qrng(99);
+static bool g_query = false;   // the buffer carries the 16 spare bytes the engine gives the view (engine.cu: file + 16 B)
+
 static int parse(bool scorer, const sttscorer::AlphabetBytes& ab, const uint8_t* p, size_t n) {
   if (scorer) {
     sttscorer::ScorerView v;
-    return sttscorer::parse_scorer(p, n, ab, &v);
+    const int e = sttscorer::parse_scorer(p, n, ab, &v);
+    if (e == 0 && g_query) {
+      // an accepted file is then USED: language-model walks and dictionary lookups (the functions the CUDA decoder
+      // compiles) over random words / states must stay inside the buffer and return
+      v.blob = p;
+      for (int q = 0; q < 40; ++q) {
+        uint32_t ids[sttscorer::kMaxOrder];
+        const int k = 1 + (int)(qrng() % v.order);
+        for (int i = 0; i < k; ++i) ids[i] = (uint32_t)(qrng() % (v.vocab_count + 1));
+        volatile double r = sttscorer::log_cond_prob_ids(v, ids, k, (qrng() & 1) != 0);
+        (void)r;
+      }
+      for (int q = 0; q < 40 && v.fst_nstates > 0; ++q) {
+        const int32_t st = (int32_t)(qrng() % (uint64_t)v.fst_nstates);
+        volatile int32_t r = sttscorer::fst_find(v, st, 1 + (int32_t)(qrng() % 255));
+        volatile bool fin = sttscorer::fst_is_final(v, st);
+        (void)r; (void)fin;
+      }
+    }
+    return e;
   }
   sttmodel::HostModel m;
   return sttmodel::load_from_buffer(p, n, &m);
@@ -51,6 +73,9 @@ int main(int argc, char** argv) {
     (parse(scorer, ab, b.data(), n) ? bad : ok)++;
   }
   std::vector<uint8_t> b(s.begin(), s.end());
+  b.resize(s.size() + 16, 0);
+  const size_t bsize = s.size();
+  g_query = true;
   for (int it = 0; it < n_flip; ++it) {
     // flatbuffer roots / KenLM and OpenFst headers sit at the ends and at section boundaries: flip near both ends and anywhere
     size_t pos[3];
@@ -58,13 +83,13 @@ int main(int argc, char** argv) {
     const int flips = 1 + (int)(rng() % 3);
     for (int k = 0; k < flips; ++k) {
       const int r = (int)(rng() % 3);
-      pos[k] = r == 0 ? rng() % std::min<size_t>(2048, b.size())
-               : r == 1 ? b.size() - 1 - rng() % std::min<size_t>(4096, b.size())
-                        : rng() % b.size();
+      pos[k] = r == 0 ? rng() % std::min<size_t>(2048, bsize)
+               : r == 1 ? bsize - 1 - rng() % std::min<size_t>(4096, bsize)
+                        : rng() % bsize;
       old[k] = b[pos[k]];
       b[pos[k]] = (uint8_t)rng();
     }
-    (parse(scorer, ab, b.data(), b.size()) ? bad : ok)++;
+    (parse(scorer, ab, b.data(), bsize) ? bad : ok)++;
     for (int k = flips - 1; k >= 0; --k) b[pos[k]] = old[k];
   }
   printf("accepted %d rejected %d\n", ok, bad);
