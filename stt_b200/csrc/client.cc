@@ -177,6 +177,9 @@ std::string metadata_to_json(const Metadata* m) {  // client.cc:125-191
 bool read_wav(const char* path, int want_rate, std::vector<short>* pcm) {
   std::ifstream f(path, std::ios::binary);
   if (!f) return false;
+  f.seekg(0, std::ios::end);
+  const unsigned long long file_size = (unsigned long long)f.tellg();
+  f.seekg(0, std::ios::beg);
   char riff[12];
   f.read(riff, 12);
   if (!f || memcmp(riff, "RIFF", 4) || memcmp(riff + 8, "WAVE", 4)) return false;
@@ -188,25 +191,33 @@ bool read_wav(const char* path, int want_rate, std::vector<short>* pcm) {
     f.read(id, 4);
     f.read(reinterpret_cast<char*>(&size), 4);
     if (!f) return false;
+    const unsigned long long here = (unsigned long long)f.tellg();
+    const unsigned long long left = file_size > here ? file_size - here : 0;
     if (!memcmp(id, "fmt ", 4)) {
+      if (size < 16 || size > left) return false;   // WAVEFORMAT: 16 bytes at least
       std::vector<char> b(size);
       f.read(b.data(), size);
+      if (!f) return false;
       memcpy(&fmt, &b[0], 2);
       memcpy(&channels, &b[2], 2);
       memcpy(&rate, &b[4], 4);
       memcpy(&bits, &b[14], 2);
+      if (size & 1) f.seekg(1, std::ios::cur);
     } else if (!memcmp(id, "data", 4)) {
       if (fmt != 1 || channels != 1 || bits != 16 || (int)rate != want_rate) {
         fprintf(stderr, "Error: audio must be WAV PCM16 mono at %d Hz (got format %u, %u ch, %u bit, %u Hz)\n", want_rate, fmt,
                 channels, bits, rate);
         return false;
       }
-      pcm->resize(size / 2);
-      f.read(reinterpret_cast<char*>(pcm->data()), size);
-      pcm->resize(f.gcount() / 2);
+      // a streamed file may announce more than it holds (0xffffffff from a pipe): take what is there, whole samples only
+      const unsigned long long bytes = (size < left ? size : left) & ~1ull;
+      pcm->resize(bytes / 2);
+      f.read(reinterpret_cast<char*>(pcm->data()), (std::streamsize)bytes);
+      pcm->resize((size_t)f.gcount() / 2);
       return true;
     } else {
-      f.seekg(size + (size & 1), std::ios::cur);
+      if (size > left) return false;
+      f.seekg((std::streamoff)size + (size & 1), std::ios::cur);
     }
   }
 }

@@ -62,3 +62,25 @@ def test_damaged_native_model(fuzz_bin, tmp_path):
     p = str(tmp_path / "m.sttw")
     open(p, "wb").write(synth.model_bytes(synth.make_weights(n_hidden=16, seed=0)))
     _run(fuzz_bin, "model", p, 0, 1500, 6000, seed=4)
+
+
+def test_damaged_wav_files_in_the_client(tmp_path):
+    """The `stt` client's WAV reader (client.cc read_wav; the reference's NO_SOX path, client.cc:390-426): short `fmt `
+    chunks, odd-sized or over-announced `data` chunks (0xffffffff from a pipe), truncated files."""
+    from conftest import LDC93S1_WAV
+    lib = os.path.join(ROOT, "stt_b200", "libstt_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("libstt_b200.so not built")
+    exe = str(tmp_path / "wav_fuzz")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+           "-I" + os.path.join(ROOT, "include"), "-o", exe, os.path.join(ROOT, "tests", "native", "wav_fuzz.cc"),
+           "-L" + os.path.join(ROOT, "stt_b200"), "-lstt_b200", "-Wl,-rpath," + os.path.join(ROOT, "stt_b200"),
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("this g++ has no sanitizer runtime")
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe, LDC93S1_WAV, str(tmp_path / "f.wav"), "6000"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stdout.startswith("samples 46797 ")
