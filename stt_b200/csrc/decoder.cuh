@@ -580,8 +580,8 @@ __global__ void decoder_init_kernel(Slot* slots, int n_slots, int32_t fst_start,
 }
 
 // ------------------------------------------------------------------------------------------------ step kernel
-// Block-wide exclusive scan of one count per thread; returns the thread's offset and the block total.
-// Barrier among the NT prefix threads of the step kernel (its helper warps never join): named barrier 1.
+// Barrier among the NT threads of the step kernel: named barrier 1 (barrier 0 is left to __syncthreads users).
+// block_scan: block-wide exclusive scan of one count per thread; returns the thread's offset and the block total.
 template <int NT>
 __device__ __forceinline__ void main_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
